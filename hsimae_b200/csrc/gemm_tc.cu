@@ -1,0 +1,648 @@
+// tcgen05 / TMEM / TMA bf16 GEMMs for sm_100a.
+//
+//   gemm_tc   : C[M,N] = A[M,K] * B[N,K]^T with fused epilogues (epilogue.cuh).
+//               Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA
+//               issuer (single elected thread, accumulators double-buffered in
+//               TMEM), warps 2..5 = epilogue (one accumulator row per thread).
+//               Operands are K-major, 128B-swizzled smem tiles of 64 K-elements.
+//   wgrad_tc  : W[Nout,Kin] += Y^T X, reduction over the token dimension, both
+//               operands MN-major (the reduction index is the slow one in
+//               memory), split over the reduction across CTAs, fp32 red.add
+//               epilogue straight into the gradient arena.
+//
+// Reference being replaced: the cuBLAS sgemm calls behind nn.Linear forward /
+// backward at /root/reference/Models.py:195-216, 232, 579, 600.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstdlib>
+#include "epilogue.cuh"
+
+namespace hsimae {
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) { printf("hsimae: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+        "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+        "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};"
+      ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+        "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
+        "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31]),
+        "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+      ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+        "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+// accumulator row of this thread in TMEM (lane = row, column = n)
+struct TmemAcc {
+  uint32_t base;  // (lane_base << 16) | column_base
+  template <int W> __device__ __forceinline__ void load(int c, float (&v)[W]) {
+    if constexpr (W == 32) ptx::tmem_ld32(base + c, v); else ptx::tmem_ld16(base + c, v);
+    ptx::tmem_ld_wait();
+  }
+  template <int W> __device__ __forceinline__ void store(int c, const float (&v)[W]) {
+    if constexpr (W == 32) ptx::tmem_st32(base + c, v); else ptx::tmem_st16(base + c, v);
+  }
+  __device__ __forceinline__ void fence_store() { ptx::tmem_st_wait(); }
+};
+
+// ---------------------------------------------------------------------------
+// descriptors
+// ---------------------------------------------------------------------------
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
+//   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1
+//   bits [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16, bf16 x bf16 -> f32, M=128.
+__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // accumulator format f32
+  d |= 1u << 7;                       // A = bf16
+  d |= 1u << 10;                      // B = bf16
+  d |= (a_mn_major ? 1u : 0u) << 15;  // A major
+  d |= (b_mn_major ? 1u : 0u) << 16;  // B major
+  d |= (uint32_t)(n >> 3) << 17;      // N / 8
+  d |= (uint32_t)(128 >> 4) << 24;    // M / 16
+  return d;
+}
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;             // 64 bf16 = one 128B swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kAccStride = 256;         // TMEM columns between the two accumulator stages
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+// ---------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p,
+               int block_n, int stages, int n_blks, int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  const uint32_t b_bytes = (uint32_t)block_n * 128u;
+  const uint32_t stage_bytes = kATileBytes + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty + stage, phase ^ 1u);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          ptx::mbar_expect_tx(full + stage, stage_bytes);
+          ptx::tma_load_2d(sa, &tmA, full + stage, kb * kBlockK, m_blk * kBlockM);
+          ptx::tma_load_2d(sa + kATileBytes, &tmB, full + stage, kb * kBlockK, n_blk * block_n);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(block_n, false, false);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty + as, aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + kATileBytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 K-elements = 32 bytes inside the 128B swizzle row
+            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty + stage);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull + as);
+        as ^= 1; if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
+      ptx::mbar_wait(tfull + as, aphase);
+      ptx::tc_fence_after();
+      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccStride};
+      const int n0 = n_blk * block_n;
+      int width = p.N - n0; if (width > block_n) width = block_n;
+      run_epilogue<EPI>(p, acc, m_blk * kBlockM + q * 32 + lane, n0, width);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty + as);
+      as ^= 1; if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------
+// wgrad kernel: one (output tile, reduction split) per CTA
+// ---------------------------------------------------------------------------
+constexpr int kBoxBytes = 64 * 128;  // one {64 x 64} bf16 TMA box
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, WgradArgs p,
+                int bn, int stages, int tiles_c, int num_tiles, int kb_total, int kb_per_split,
+                uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  const uint32_t a_bytes = 2 * kBoxBytes;
+  const uint32_t b_bytes = (uint32_t)(bn / 64) * kBoxBytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % num_tiles;
+  const int split = blockIdx.x / num_tiles;
+  const int r_blk = tile / tiles_c, c_blk = tile - r_blk * tiles_c;
+  const int kb0 = split * kb_per_split;
+  int kb1 = kb0 + kb_per_split; if (kb1 > kb_total) kb1 = kb_total;
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmY);
+    ptx::prefetch_tmap(&tmX);
+    for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    ptx::mbar_init(tfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(empty + stage, phase ^ 1u);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          ptx::mbar_expect_tx(full + stage, stage_bytes);
+          for (int j = 0; j < 2; ++j)
+            ptx::tma_load_2d(sa + j * kBoxBytes, &tmY, full + stage, r_blk * kBlockM + j * 64, kb * 64);
+          for (int j = 0; j < bn / 64; ++j)
+            ptx::tma_load_2d(sa + a_bytes + j * kBoxBytes, &tmX, full + stage, c_blk * bn + j * 64, kb * 64);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(bn, true, true);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(full + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * kstep_bytes, lbo, sbo);
+            const uint64_t bdesc = make_smem_desc(sa + a_bytes + k * kstep_bytes, lbo, sbo);
+            ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty + stage);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull);
+      }
+    } else {
+      const int q = warp & 3;
+      ptx::mbar_wait(tfull, 0);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int r = r_blk * kBlockM + q * 32 + lane;  // packed output row
+      float* drow = nullptr;
+      if (r < p.Nout) {
+        if (p.row_map == 0) {
+          if (r < p.rows_valid) drow = p.dst0 + (size_t)r * p.ld;
+        } else {
+          const int which = (r % (2 * kGate)) / kGate;
+          const int h = (r / (2 * kGate)) * kGate + (r % kGate);
+          if (h < p.rows_valid) drow = (which ? p.dst1 : p.dst0) + (size_t)h * p.ld;
+        }
+      }
+      for (int c = 0; c < bn; c += 16) {
+        float v[16];
+        ptx::tmem_ld16(tbase + c, v);
+        ptx::tmem_ld_wait();
+        const int col = c_blk * bn + c;
+        if (drow != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            if (col + i < p.cols_valid) red_add_f32x4(drow + col + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
+}
+
+// ---------------------------------------------------------------------------
+// column sums (bias gradients): dst[map(n)] += sum_m Y[m][n]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ Y, int ldy, int Mred, int Nout, int rows_per_cta,
+              float* dst0, float* dst1, int row_map, int rows_valid) {
+  __shared__ float part[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 64 + lane * 2;
+  const int m0 = blockIdx.y * rows_per_cta;
+  int m1 = m0 + rows_per_cta; if (m1 > Mred) m1 = Mred;
+  float s0 = 0.f, s1 = 0.f;
+  if (n < Nout) {
+    for (int m = m0 + warp; m < m1; m += 8) {
+      uint32_t u = *reinterpret_cast<const uint32_t*>(Y + (size_t)m * ldy + n);
+      float2 f = unpack_bf16x2(u);
+      s0 += f.x; s1 += f.y;
+    }
+  }
+  part[warp][lane * 2] = s0; part[warp][lane * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][threadIdx.x];
+    const int r = blockIdx.x * 64 + threadIdx.x;
+    if (r < Nout) {
+      if (row_map == 0) { if (r < rows_valid) atomicAdd(dst0 + r, s); }
+      else {
+        const int which = (r % (2 * kGate)) / kGate;
+        const int h = (r / (2 * kGate)) * kGate + (r % kGate);
+        if (h < rows_valid) atomicAdd((which ? dst1 : dst0) + h, s);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: tensor-map cache + launchers
+// ---------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; uint64_t d0, d1, pitch; uint32_t b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && pitch == o.pitch && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.d0); mix(k.d1); mix(k.pitch); mix(k.b0); mix(k.b1);
+    return h;
+  }
+};
+
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D bf16 tensor, dim0 contiguous (d0 elements), d1 rows of `pitch` elements, box {b0, b1}, 128B swizzle.
+int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t b0, uint32_t b1, CUtensorMap* out) {
+  MapKey key{ptr, d0, d1, pitch, b0, b1};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return kOk; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return kCudaError; }
+  HS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand %p is not 16-byte aligned", ptr);
+  HS_REQUIRE((pitch * 2) % 16 == 0, "TMA operand pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)pitch);
+  HS_REQUIRE(b0 * 2 == 128 && b1 <= 256, "bad TMA box {%u,%u}", b0, b1);
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {pitch * 2};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p dims={%llu,%llu} pitch=%llu box={%u,%u}", (int)r, ptr,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)pitch, b0, b1);
+    return kCudaError;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_maps.size() > 65536) g_maps.clear();
+    g_maps[key] = m;
+  }
+  *out = m;
+  return kOk;
+}
+
+template <int EPI>
+int launch_gemm(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, int block_n, int stages, int n_blks,
+                int num_tiles, size_t smem, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  gemm_tc_kernel<EPI><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, a, block_n, stages, n_blks, num_tiles);
+  HS_CHECK_LAUNCH("gemm_tc_kernel");
+  return kOk;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+}  // namespace
+
+int gemm_check_args(const GemmArgs& a, int epi) {
+  HS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  HS_REQUIRE(a.N % 16 == 0, "gemm: N=%d must be a multiple of 16", a.N);
+  HS_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm: lda=%d ldb=%d must be multiples of 8", a.lda, a.ldb);
+  HS_REQUIRE(epi >= 0 && epi < kNumEpilogues, "gemm: bad epilogue %d", epi);
+  if (epi == kEpiResidLN) {
+    HS_REQUIRE(a.N <= 256, "gemm: residual/LayerNorm epilogue needs the row in one tile (N=%d > 256)", a.N);
+    HS_REQUIRE(a.resid != nullptr, "gemm: residual epilogue without residual");
+  }
+  if (epi == kEpiSwiGLU) HS_REQUIRE(a.N % 32 == 0 && a.out1 != nullptr, "gemm: SwiGLU epilogue needs N%%32==0 and out1");
+  if (epi == kEpiDSwiGLU) HS_REQUIRE(a.ab != nullptr, "gemm: dSwiGLU epilogue needs saved pre-activations");
+  return kOk;
+}
+
+int pick_block_n(int N, int epi) {
+  if (epi == kEpiResidLN) return N;
+  if (N <= 256) return N;
+  // prefer the widest tile that wastes least on the tail
+  int best = 256, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 128; bn -= 32) {
+    int waste = ceil_div(N, bn) * bn - N;
+    if (waste < best_waste) { best = bn; best_waste = waste; }
+  }
+  return best;
+}
+
+int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
+  HS_TRY(gemm_check_args(a, epi));
+  const int block_n = pick_block_n(a.N, epi);
+  const int n_blks = ceil_div(a.N, block_n);
+  const int m_blks = ceil_div(a.M, kBlockM);
+  const int num_tiles = n_blks * m_blks;
+  const int stage_bytes = kATileBytes + block_n * 128;
+  int stages = kSmemBudget / stage_bytes;
+  if (stages > 8) stages = 8;
+  const int num_kb = ceil_div(a.K, kBlockK);
+  if (stages > num_kb * 2) stages = num_kb * 2 < 2 ? 2 : num_kb * 2;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  CUtensorMap tmA, tmB;
+  HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tmA));
+  HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)block_n, &tmB));
+  switch (epi) {
+    case kEpiBiasBf16: return launch_gemm<kEpiBiasBf16>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+    case kEpiBiasF32:  return launch_gemm<kEpiBiasF32>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+    case kEpiResidLN:  return launch_gemm<kEpiResidLN>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+    case kEpiSwiGLU:   return launch_gemm<kEpiSwiGLU>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+    case kEpiDSwiGLU:  return launch_gemm<kEpiDSwiGLU>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+  }
+  set_error("gemm: bad epilogue %d", epi);
+  return kInvalidArgument;
+}
+
+int wgrad_check_args(const WgradArgs& a) {
+  HS_REQUIRE(a.Mred > 0 && a.Nout > 0 && a.Kin > 0, "wgrad: empty problem");
+  HS_REQUIRE(a.ldy % 8 == 0 && a.ldx % 8 == 0, "wgrad: ldy=%d ldx=%d must be multiples of 8", a.ldy, a.ldx);
+  HS_REQUIRE(a.ld % 4 == 0 && a.cols_valid % 4 == 0, "wgrad: destination ld=%d cols=%d must be multiples of 4", a.ld, a.cols_valid);
+  HS_REQUIRE(a.row_map == 0 || (a.row_map == 1 && a.dst1 != nullptr), "wgrad: bad row map");
+  return kOk;
+}
+
+int launch_colsum(const WgradArgs& a, cudaStream_t stream) {
+  if (!a.bias0) return kOk;
+  int gx = ceil_div(a.Nout, 64);
+  int gy = ceil_div(2 * kNumSMs, gx);
+  int rows = ceil_div(a.Mred, gy);
+  if (rows < 64) rows = 64;
+  gy = ceil_div(a.Mred, rows);
+  colsum_kernel<<<dim3(gx, gy), 256, 0, stream>>>(a.Y, a.ldy, a.Mred, a.Nout, rows, a.bias0, a.bias1, a.row_map, a.rows_valid);
+  HS_CHECK_LAUNCH("colsum_kernel");
+  return kOk;
+}
+
+int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
+  HS_TRY(wgrad_check_args(a));
+  static bool configured = false;
+  if (!configured) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  // output-column tile: multiple of 64, at most 256
+  int kin64 = ceil_div(a.Kin, 64) * 64;
+  int tiles_c = ceil_div(kin64, 256);
+  int bn = ceil_div(kin64 / 64, tiles_c) * 64;
+  const int tiles_r = ceil_div(a.Nout, kBlockM);
+  const int num_tiles = tiles_r * tiles_c;
+  const int kb_total = ceil_div(a.Mred, 64);
+  int splits = ceil_div(kNumSMs, num_tiles);
+  if (splits > kb_total) splits = kb_total;
+  const int kb_per = ceil_div(kb_total, splits);
+  splits = ceil_div(kb_total, kb_per);
+  const int stage_bytes = (2 + bn / 64) * kBoxBytes;
+  int stages = kSmemBudget / stage_bytes;
+  if (stages > 8) stages = 8;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  CUtensorMap tmY, tmX;
+  HS_TRY(get_tmap(a.Y, (uint64_t)a.Nout, (uint64_t)a.Mred, (uint64_t)a.ldy, 64, 64, &tmY));
+  HS_TRY(get_tmap(a.X, (uint64_t)a.Kin, (uint64_t)a.Mred, (uint64_t)a.ldx, 64, 64, &tmX));
+  // MN-major SWIZZLE_128B canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units:
+  // LBO = distance between 64-element atoms along M/N (one TMA box = 8 KB),
+  // SBO = distance between groups of 8 reduction rows (1 KB); a K=16 step spans two groups.
+  const uint32_t lbo = (uint32_t)env_int("HSIMAE_WGRAD_LBO", kBoxBytes);
+  const uint32_t sbo = (uint32_t)env_int("HSIMAE_WGRAD_SBO", 1024);
+  const uint32_t kstep = (uint32_t)env_int("HSIMAE_WGRAD_KSTEP", 2048);
+  wgrad_tc_kernel<<<num_tiles * splits, kGemmThreads, smem, stream>>>(tmY, tmX, a, bn, stages, tiles_c, num_tiles, kb_total,
+                                                                      kb_per, lbo, sbo, kstep);
+  HS_CHECK_LAUNCH("wgrad_tc_kernel");
+  return launch_colsum(a, stream);
+}
+
+}  // namespace hsimae

@@ -1,0 +1,253 @@
+// Structured spatial-spectral masking and the fused patch-embedding kernels.
+#include "kernels.cuh"
+
+namespace hsimae {
+
+// ---------------------------------------------------------------------------
+// Masking.  Reference: Models.py:495-535 (three argsort/argsort/gather rounds).
+// Restated per sample as: rank the T spectral noises and the L spatial noises
+// (stable, lowest index first); a token (t,l) is visible iff rank_t < len_t and
+// rank_l < len_l; ids_shuffle lists tokens by (#dropped axes, raster index).
+// Integer outputs are bit-exact with the reference (tests/test_mask_*).
+// ---------------------------------------------------------------------------
+constexpr int kMaxT = 32, kMaxL = 64;
+
+__global__ void __launch_bounds__(128)
+mask_kernel(const float* __restrict__ noise_t, const float* __restrict__ noise_l, int N, int T, int L, int len_t,
+            int len_l, int64_t* __restrict__ ids_keep, int64_t* __restrict__ ids_restore, float* __restrict__ mask,
+            int32_t* __restrict__ ids_keep32, int32_t* __restrict__ ids_restore32) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* nt = noise_t + (size_t)n * T;
+  const float* nl = noise_l + (size_t)n * L;
+  uint32_t keep_t = 0;
+  uint64_t keep_l = 0;
+  for (int i = 0; i < T; ++i) {
+    const float v = nt[i];
+    int rank = 0;
+    for (int j = 0; j < T; ++j) { const float w = nt[j]; rank += (w < v) || (w == v && j < i); }
+    if (rank < len_t) keep_t |= 1u << i;
+  }
+  for (int i = 0; i < L; ++i) {
+    const float v = nl[i];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) { const float w = nl[j]; rank += (w < v) || (w == v && j < i); }
+    if (rank < len_l) keep_l |= 1ull << i;
+  }
+  const int P = T * L;
+  const int K = len_t * len_l;
+  const int n1 = len_t * (L - len_l) + (T - len_t) * len_l;  // tokens dropped on exactly one axis
+  int c0 = 0, c1 = K, c2 = K + n1;
+  for (int t = 0; t < T; ++t) {
+    const int dt = (keep_t >> t) & 1u ? 0 : 1;
+    for (int l = 0; l < L; ++l) {
+      const int dropped = dt + ((keep_l >> l) & 1ull ? 0 : 1);
+      const int p = t * L + l;
+      int pos;
+      if (dropped == 0) {
+        pos = c0++;
+        ids_keep[(size_t)n * K + pos] = p;
+        if (ids_keep32) ids_keep32[(size_t)n * K + pos] = p;
+      } else if (dropped == 1) pos = c1++;
+      else pos = c2++;
+      ids_restore[(size_t)n * P + p] = pos;
+      if (ids_restore32) ids_restore32[(size_t)n * P + p] = pos;
+      mask[(size_t)n * P + p] = dropped ? 1.0f : 0.0f;
+    }
+  }
+}
+
+int launch_mask(const float* noise_t, const float* noise_l, int N, int T, int L, int len_t, int len_l,
+                int64_t* ids_keep, int64_t* ids_restore, float* mask, int32_t* ids_keep32, int32_t* ids_restore32,
+                cudaStream_t stream) {
+  HS_REQUIRE(N >= 0 && T >= 1 && T <= kMaxT && L >= 1 && L <= kMaxL, "mask: unsupported shape N=%d T=%d L=%d", N, T, L);
+  HS_REQUIRE(len_t >= 1 && len_t <= T && len_l >= 1 && len_l <= L, "mask: bad visible shape (%d,%d)", len_t, len_l);
+  if (N == 0) return kOk;
+  mask_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(noise_t, noise_l, N, T, L, len_t, len_l, ids_keep, ids_restore, mask,
+                                                    ids_keep32, ids_restore32);
+  HS_CHECK_LAUNCH("mask_kernel");
+  return kOk;
+}
+
+// ---------------------------------------------------------------------------
+// Patch embedding forward.  Reference: Conv3d(stride==kernel) + 'ncts->ntsc'
+// (Models.py:147-158), gather of the visible tokens (:528), + pos_embed gather
+// (:547-550), followed by the first LayerNorm of the consuming block(s)
+// (Block.forward :304).  One CTA walks samples; the cube is read once with
+// coalesced 128-bit loads, only visible tokens are embedded.
+// ---------------------------------------------------------------------------
+constexpr int kEmbedThreads = 256;
+constexpr int kTokChunk = 12;
+
+__device__ __forceinline__ int cube_index(const PatchGeom& g, int p, int j) {
+  // token p = (t, h, w); element j = (u, pp, q)  (Models.py:469-471)
+  const int t = p / g.L, hw = p - t * g.L;
+  const int h = hw / g.G, w = hw - h * g.G;
+  const int pp2 = g.p * g.p;
+  const int u = j / pp2, r = j - u * pp2;
+  const int pp = r / g.p, q = r - pp * g.p;
+  return ((t * g.u + u) * g.img + (h * g.p + pp)) * g.img + (w * g.p + q);
+}
+
+__global__ void __launch_bounds__(kEmbedThreads)
+embed_fwd_kernel(EmbedArgs a) {
+  extern __shared__ float sm[];
+  const PatchGeom g = a.g;
+  const int D = a.D, K = a.K, PK = g.PK;
+  float* sW = sm;                         // [PK][D]  (transposed weight)
+  float* sCube = sW + (size_t)PK * D;     // [cube]
+  float* sX = sCube + g.cube;             // [K][D]
+  int* sIdx = reinterpret_cast<int*>(sX + (size_t)K * D);  // [K][PK] cube offsets of the kept tokens
+  int* sTok = sIdx + (size_t)K * PK;      // [K]
+
+  for (int i = threadIdx.x; i < PK * D; i += blockDim.x) {
+    const int d = i / PK, j = i - d * PK;
+    sW[(size_t)j * D + d] = a.W[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
+    for (int i = threadIdx.x; i < g.cube / 4; i += blockDim.x) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sTok[i] = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * PK; i += blockDim.x) {
+      const int k = i / PK, j = i - k * PK;
+      sIdx[i] = cube_index(g, sTok[k], j);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float b = a.bias ? a.bias[d] : 0.f;
+      for (int k0 = 0; k0 < K; k0 += kTokChunk) {
+        float acc[kTokChunk];
+#pragma unroll
+        for (int k = 0; k < kTokChunk; ++k) acc[k] = 0.f;
+        for (int j = 0; j < PK; ++j) {
+          const float w = sW[(size_t)j * D + d];
+#pragma unroll
+          for (int k = 0; k < kTokChunk; ++k)
+            if (k0 + k < K) acc[k] = fmaf(sCube[sIdx[(k0 + k) * PK + j]], w, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kTokChunk; ++k)
+          if (k0 + k < K) sX[(size_t)(k0 + k) * D + d] = acc[k] + b + __ldg(a.pos + (size_t)sTok[k0 + k] * D + d);
+      }
+    }
+    __syncthreads();
+    // LayerNorm(s) + stores, one warp per token
+    for (int k = warp; k < K; k += nwarps) {
+      const float* xr = sX + (size_t)k * D;
+      const size_t m = (size_t)n * K + k;
+      float s = 0.f;
+      for (int i = lane; i < D; i += 32) s += xr[i];
+      const float mean = warp_sum(s) / D;
+      float sq = 0.f;
+      for (int i = lane; i < D; i += 32) { const float dv = xr[i] - mean; sq = fmaf(dv, dv, sq); }
+      const float rstd = rsqrtf(warp_sum(sq) / D + a.eps);
+      for (int i = lane; i < D; i += 32) {
+        const float v = xr[i];
+        a.x[m * D + i] = v;
+        const float xh = (v - mean) * rstd;
+        if (a.ln_a) a.ln_a[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_a[i], a.beta_a[i]));
+        if (a.ln_b) a.ln_b[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_b[i], a.beta_b[i]));
+      }
+      if (lane == 0) {
+        if (a.stats_a) { a.stats_a[2 * m] = mean; a.stats_a[2 * m + 1] = rstd; }
+        if (a.stats_b) { a.stats_b[2 * m] = mean; a.stats_b[2 * m + 1] = rstd; }
+      }
+    }
+  }
+}
+
+static size_t embed_fwd_smem(const EmbedArgs& a) {
+  return ((size_t)a.g.PK * a.D + a.g.cube + (size_t)a.K * a.D) * sizeof(float) + ((size_t)a.K * a.g.PK + a.K) * sizeof(int);
+}
+
+int launch_embed_fwd(const EmbedArgs& a, cudaStream_t stream) {
+  HS_REQUIRE(a.g.cube % 4 == 0, "embed: cube size %d must be a multiple of 4", a.g.cube);
+  HS_REQUIRE(a.K >= 1 && a.K <= a.g.P, "embed: bad K=%d", a.K);
+  if (a.N == 0) return kOk;
+  const size_t smem = embed_fwd_smem(a);
+  HS_REQUIRE(smem <= 227 * 1024, "embed: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
+  HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = a.N < kNumSMs ? a.N : kNumSMs;
+  embed_fwd_kernel<<<grid, kEmbedThreads, smem, stream>>>(a);
+  HS_CHECK_LAUNCH("embed_fwd_kernel");
+  return kOk;
+}
+
+// ---------------------------------------------------------------------------
+// Patch embedding backward: dW[d][j] += sum_m dx[m][d] * patch[m][j], db[d] += sum_m dx[m][d].
+// (autograd of Models.py:157; the input needs no gradient.)
+// Each thread owns one output channel d and PK accumulators; CTAs walk samples
+// and flush with one atomicAdd per (d, j).
+// ---------------------------------------------------------------------------
+constexpr int kMaxPK = 128;
+
+template <int PKC>
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(EmbedBwdArgs a) {
+  extern __shared__ float sm[];
+  const PatchGeom g = a.g;
+  const int D = a.D, K = a.K, PK = g.PK;
+  float* sCube = sm;
+  int* sIdx = reinterpret_cast<int*>(sCube + g.cube);
+  int* sTok = sIdx + (size_t)K * PK;
+  // channel handled by this thread (D may exceed blockDim: loop over channel groups)
+  for (int d0 = 0; d0 < D; d0 += blockDim.x) {
+    const int d = d0 + threadIdx.x;
+    float acc[PKC];
+#pragma unroll
+    for (int j = 0; j < PKC; ++j) acc[j] = 0.f;
+    float bsum = 0.f;
+    for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+      __syncthreads();
+      const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
+      for (int i = threadIdx.x; i < g.cube / 4; i += blockDim.x) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+      for (int i = threadIdx.x; i < K; i += blockDim.x) sTok[i] = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
+      __syncthreads();
+      for (int i = threadIdx.x; i < K * PK; i += blockDim.x) {
+        const int k = i / PK, j = i - k * PK;
+        sIdx[i] = cube_index(g, sTok[k], j);
+      }
+      __syncthreads();
+      if (d < D) {
+        for (int k = 0; k < K; ++k) {
+          const size_t m = (size_t)n * K + k;
+          float gv = a.dx_a[m * D + d];
+          if (a.dx_b) gv += a.dx_b[m * D + d];
+          bsum += gv;
+#pragma unroll
+          for (int j = 0; j < PKC; ++j)
+            if (j < PK) acc[j] = fmaf(gv, sCube[sIdx[k * PK + j]], acc[j]);
+        }
+      }
+    }
+    if (d < D) {
+#pragma unroll
+      for (int j = 0; j < PKC; ++j)
+        if (j < PK) atomicAdd(a.dW + (size_t)d * PK + j, acc[j]);
+      if (a.dbias) atomicAdd(a.dbias + d, bsum);
+    }
+  }
+}
+
+int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream) {
+  HS_REQUIRE(a.g.PK <= kMaxPK, "embed_bwd: patch of %d elements unsupported (max %d)", a.g.PK, kMaxPK);
+  if (a.N == 0) return kOk;
+  const size_t smem = (size_t)a.g.cube * sizeof(float) + ((size_t)a.K * a.g.PK + a.K) * sizeof(int);
+  HS_REQUIRE(smem <= 227 * 1024, "embed_bwd: needs %zu bytes of shared memory", smem);
+  const int grid = a.N < kNumSMs ? a.N : kNumSMs;
+  if (a.g.PK <= 72) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    embed_bwd_kernel<72><<<grid, 256, smem, stream>>>(a);
+  } else {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<kMaxPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    embed_bwd_kernel<kMaxPK><<<grid, 256, smem, stream>>>(a);
+  }
+  HS_CHECK_LAUNCH("embed_bwd_kernel");
+  return kOk;
+}
+
+}  // namespace hsimae

@@ -1,0 +1,156 @@
+/* hsimae_b200 -- C ABI of the B200 (sm_100a) HSIMAE compute library.
+ *
+ * Drop-in boundary: the reference (Ryan21wy/HSIMAE) has no FFI/plugin layer; its
+ * only stable interface is the Python module `Models` (HSIMAE, DualViT, HSIViT;
+ * /root/reference/Models.py:309-634, 637-993, 996-1160).  The repo-root
+ * `Models.py` mirrors that surface and drives the functions below through
+ * ctypes with raw device pointers, explicit sizes and an explicit cudaStream_t.
+ * No torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero otherwise; the message is
+ *     available (thread-local) from hsimae_last_error().
+ *   - the caller owns every buffer (parameters, arenas, workspaces, outputs);
+ *     the library allocates no device memory and keeps only cached TMA
+ *     descriptors keyed by pointer/shape.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     function synchronises, so the call sequence is CUDA-graph capturable.
+ *   - all matrices are row-major; "bf16" is __nv_bfloat16; token rows of a
+ *     sample are ordered (spectral group t, spatial position l), l fastest.
+ */
+#ifndef HSIMAE_B200_H_
+#define HSIMAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSIMAE_ABI_VERSION 1
+
+/* Constructor arguments of the reference model classes that shape the compute
+ * path (Models.py:312-332, 640-663, 997-1016). */
+typedef struct hsimae_dims {
+  int32_t img_size, patch_size, bands, b_patch_size;
+  int32_t embed_dim, depth, s_depth, num_heads;
+  int32_t dec_dim, dec_depth, dec_heads; /* dec_dim == 0: no decoder (HSIViT) */
+  int32_t num_class;                     /* 0: no classification head (HSIMAE) */
+  int32_t qkv_bias;                      /* !no_qkv_bias */
+  int32_t norm_pix_loss;
+  float mlp_ratio;
+} hsimae_dims;
+
+typedef struct hsimae_plan hsimae_plan;
+
+const char* hsimae_last_error(void);
+int hsimae_abi_version(void);
+
+/* ---- plan: static layout of parameters, packed operands and gradients ---- */
+int hsimae_plan_create(const hsimae_dims* dims, hsimae_plan** out);
+void hsimae_plan_destroy(hsimae_plan* plan);
+
+/* Parameter table, in the library's canonical order.  Names are the reference's
+ * state_dict keys (Models.py:342-424, 736).  `has_grad` is 0 for the frozen
+ * position tables (Models.py:434-435). */
+int hsimae_plan_num_params(const hsimae_plan* plan);
+const char* hsimae_plan_param_name(const hsimae_plan* plan, int i);
+int64_t hsimae_plan_param_numel(const hsimae_plan* plan, int i);
+int64_t hsimae_plan_param_grad_offset(const hsimae_plan* plan, int i); /* fp32 elements into the gradient arena; -1 if none */
+int hsimae_plan_param_has_grad(const hsimae_plan* plan, int i);
+int64_t hsimae_plan_grad_arena_elems(const hsimae_plan* plan);  /* fp32 elements */
+int64_t hsimae_plan_bf16_arena_elems(const hsimae_plan* plan);  /* packed GEMM operands */
+int64_t hsimae_plan_f32_arena_elems(const hsimae_plan* plan);   /* packed biases / affine / tables */
+int64_t hsimae_plan_pack_table_bytes(const hsimae_plan* plan);  /* device scratch for the packing job table */
+int hsimae_plan_hidden(const hsimae_plan* plan, int decoder);   /* SwiGLU hidden width (Models.py:225) */
+/* Gradient arena regions in the order their gradients are final during backward:
+ * i = 3 decoder (after hsimae_decoder_backward), 2 fusion+norm+head (encoder stage 1),
+ * 1 spectral encoder (stage 2), 0 patch embedding + spatial encoder (stage 4).
+ * Lets the caller all-reduce one region while the next stage is still computing. */
+int hsimae_plan_grad_bucket(const hsimae_plan* plan, int i, int64_t* offset, int64_t* elems);
+
+/* fp32 master parameters -> packed bf16/fp32 arenas (both zero-initialised by
+ * the caller once).  `params` is a HOST array of num_params device pointers. */
+int hsimae_pack_params(hsimae_plan* plan, const void* const* params, void* bf16_arena, void* f32_arena,
+                       void* pack_table_dev, void* stream);
+
+/* ---- masking: replaces HSIMAE.spatial_spectral_masking (Models.py:495-535) ---- */
+int hsimae_mask(const float* noise_t, const float* noise_l, int32_t n, int32_t T, int32_t L, int32_t len_t, int32_t len_l,
+                int64_t* ids_keep, int64_t* ids_restore, float* mask, int32_t* ids_keep32, int32_t* ids_restore32,
+                void* stream);
+
+/* ---- encoder: replaces forward_encoder (Models.py:537-571, 869-894, 896-923, 1119-1145)
+ * ids_keep32 == NULL selects the unmasked pass (len_t = T, len_l = L).
+ * `drop` is NULL or a host array of 2*(2*s_depth+n_fusion) device pointers to the
+ * already-scaled stochastic-depth factors, ordered blocks_1[i].{attn,mlp}...,
+ * blocks_2[i]..., blocks[i]...; NULL entries mean identity (Models.py:235-251). */
+int64_t hsimae_encoder_workspace_bytes(const hsimae_plan* plan, int32_t n, int32_t len_t, int32_t len_l, int32_t save);
+int hsimae_encoder_forward(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, const float* imgs, int32_t n,
+                           int32_t len_t, int32_t len_l, const int32_t* ids_keep32, const float* const* drop, int32_t save,
+                           void* ws, int64_t ws_bytes, void* stream);
+/* consumes the latent gradient left in the workspace by decoder/head backward.
+ * `stages` is a bit mask (1: final norm + fusion blocks, 2: spectral encoder,
+ * 4: spatial encoder + patch embedding); stages must be run in that order, 7 = all. */
+int hsimae_encoder_backward(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, const float* imgs, int32_t n,
+                            int32_t len_t, int32_t len_l, const int32_t* ids_keep32, const float* const* drop, void* ws,
+                            int64_t ws_bytes, float* grad_arena, int32_t stages, void* stream);
+/* copy of the final-norm output (fp32 [n*K, D]) for inspection / parity tests */
+int hsimae_encoder_latent(const hsimae_plan* plan, int32_t n, int32_t len_t, int32_t len_l, int32_t save, const void* f32_arena,
+                          const void* ws, float* out, void* stream);
+
+/* ---- decoder + loss + pixel outputs: forward_decoder, forward_loss, recons (Models.py:573-625) ---- */
+int64_t hsimae_decoder_workspace_bytes(const hsimae_plan* plan, int32_t n, int32_t len_t, int32_t len_l, int32_t save);
+int hsimae_decoder_forward(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, const float* imgs, int32_t n,
+                           int32_t len_t, int32_t len_l, const int32_t* ids_restore32, const float* mask, const void* enc_ws,
+                           int32_t enc_save, int32_t save, void* ws, int64_t ws_bytes, float* loss, float* pred_img,
+                           float* mask_img, float* pred_tokens, void* stream);
+/* grad_loss: device pointer to the scalar dL/dloss.  Leaves dL/dlatent in enc_ws. */
+int hsimae_decoder_backward(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, int32_t n, int32_t len_t,
+                            int32_t len_l, const int32_t* ids_restore32, void* enc_ws, void* ws, int64_t ws_bytes,
+                            const float* grad_loss, float* grad_arena, void* stream);
+
+/* ---- classification head: DualViT.head / HSIViT.head 'AGG' (Models.py:964-973, 1147-1156) ---- */
+int hsimae_head_forward(hsimae_plan* plan, const void* f32_arena, int32_t n, const void* enc_ws, int32_t enc_save, float* pooled,
+                        float* logits, void* stream);
+int hsimae_head_backward(hsimae_plan* plan, const void* f32_arena, int32_t n, void* enc_ws, const float* pooled,
+                         const float* dlogits, float* grad_arena, void* stream);
+
+/* ---- single operators (unit parity tests; also the building blocks above) ---- */
+/* C[M,N] = A[M,K] * B[N,K]^T with a fused epilogue (see csrc/gemm.cuh).  impl 0 = tcgen05, 1 = CUDA-core checker. */
+typedef struct hsimae_gemm_desc {
+  int32_t M, N, K, epilogue, impl;
+  const void* A; int32_t lda;
+  const void* B; int32_t ldb;
+  void* out0; int32_t ld0;
+  void* out1; int32_t ld1;
+  const float* bias;
+  const float* resid; int32_t ldr;
+  const float* resid2;
+  const float* gamma; const float* beta; float* stats;
+  const void* ab; int32_t ldab;
+  const float* rowscale; int32_t rs_mode, rs_K, rs_len_l, rs_G;
+  float* scratch; /* impl 1: fp32 [M,N] */
+} hsimae_gemm_desc;
+int hsimae_gemm(const hsimae_gemm_desc* d, void* stream);
+
+/* W[Nout,Kin] += Y[Mred,Nout]^T X[Mred,Kin] (+ column sums of Y into bias).  row_map 1 = interleaved w1|w3 rows. */
+typedef struct hsimae_wgrad_desc {
+  int32_t Mred, Nout, Kin, impl;
+  const void* Y; int32_t ldy;
+  const void* X; int32_t ldx;
+  float* dst0; float* dst1; int32_t ld, row_map, rows_valid, cols_valid;
+  float* bias0; float* bias1;
+} hsimae_wgrad_desc;
+int hsimae_wgrad(const hsimae_wgrad_desc* d, void* stream);
+
+int hsimae_attention_forward(const void* qkv, void* out, float* lse, int32_t n, int32_t D, int32_t heads, int32_t K, int32_t nseq,
+                             int32_t len, int32_t seq_step, int32_t tok_step, void* stream);
+int hsimae_attention_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int32_t n,
+                              int32_t D, int32_t heads, int32_t K, int32_t nseq, int32_t len, int32_t seq_step,
+                              int32_t tok_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSIMAE_B200_H_ */
