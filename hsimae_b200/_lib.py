@@ -47,6 +47,7 @@ class WgradDesc(C.Structure):
 PROTOTYPES = {
     "hsimae_last_error": (C.c_char_p, []),
     "hsimae_abi_version": (c_int, []),
+    "hsimae_launch_count": (c_i64, []),
     "hsimae_plan_create": (c_int, [C.POINTER(Dims), C.POINTER(c_void_p)]),
     "hsimae_plan_destroy": (None, [c_void_p]),
     "hsimae_plan_num_params": (c_int, [c_void_p]),

@@ -37,8 +37,12 @@ const char* last_error();
     }                                                                                   \
   } while (0)
 
+void count_launch();
+long long launch_count();
+
 #define HS_CHECK_LAUNCH(name)                                                           \
   do {                                                                                  \
+    ::hsimae::count_launch();                                                           \
     cudaError_t _e = cudaGetLastError();                                                \
     if (_e != cudaSuccess) {                                                            \
       ::hsimae::set_error("launch of %s failed: %s (%s:%d)", name,                      \

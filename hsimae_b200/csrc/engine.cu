@@ -485,6 +485,7 @@ extern "C" {
 
 const char* hsimae_last_error(void) { return hsimae::last_error(); }
 int hsimae_abi_version(void) { return HSIMAE_ABI_VERSION; }
+int64_t hsimae_launch_count(void) { return (int64_t)hsimae::launch_count(); }
 
 int hsimae_plan_create(const hsimae_dims* dims, hsimae_plan** out) {
   HS_REQUIRE(dims && out, "null argument");

@@ -1,4 +1,5 @@
 // thread-local error message storage for the C ABI
+#include <atomic>
 #include "common.cuh"
 
 namespace hsimae {
@@ -13,5 +14,10 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 }  // namespace hsimae

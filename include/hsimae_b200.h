@@ -46,6 +46,8 @@ typedef struct hsimae_plan hsimae_plan;
 
 const char* hsimae_last_error(void);
 int hsimae_abi_version(void);
+/* number of kernels launched by this library so far in this process */
+int64_t hsimae_launch_count(void);
 
 /* ---- plan: static layout of parameters, packed operands and gradients ---- */
 int hsimae_plan_create(const hsimae_dims* dims, hsimae_plan** out);

@@ -1,0 +1,232 @@
+"""GPU: single-kernel parity.  tcgen05 GEMMs vs the CUDA-core checker vs a torch fp32 reference of the
+same op (inputs are the same bf16 values, so differences are accumulation order + output rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from oracle import hsimae_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# bf16 output rounding is 2^-9 relative; fp32 accumulation-order differences are ~1e-6
+TOL_BF16 = 6e-3
+TOL_F32 = 2e-5
+
+
+def _rand_bf16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (scale * torch.randn(*shape, device=DEV, generator=g)).to(torch.bfloat16)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from hsimae_b200 import ops
+    return ops
+
+
+# ---------------------------------------------------------------- mask
+@pytest.mark.parametrize("n,T,L,lt,ll", [(64, 4, 9, 3, 6), (64, 4, 9, 2, 9), (4096, 4, 9, 3, 6), (33, 4, 9, 2, 4), (33, 4, 9, 4, 2),
+                                         (7, 4, 9, 3, 3), (5, 4, 9, 2, 2), (9, 4, 9, 4, 9), (16, 8, 16, 3, 5), (1, 2, 4, 2, 2)])
+def test_mask_bit_exact(ops, n, T, L, lt, ll):
+    torch.manual_seed(n + lt)
+    nt, nl = torch.rand(n, T), torch.rand(n, L)
+    if n > 2:  # exact ties (undefined in the reference; lowest index first here)
+        nt[1, 1] = nt[1, 0]
+        nl[2, L - 1] = nl[2, 0]
+        nl[0, :] = 0.5
+    k, r, m = ops.mask(nt.to(DEV), nl.to(DEV), lt, ll)
+    ko, ro, mo = O.structured_mask(nt, nl, lt, ll)
+    assert k.dtype == torch.int64 and r.dtype == torch.int64 and m.dtype == torch.float32
+    assert torch.equal(k.cpu(), ko) and torch.equal(r.cpu(), ro) and torch.equal(m.cpu(), mo)
+
+
+def test_mask_kat(ops, golden):
+    import hashlib
+    z = golden("kat_masks.npz")
+    k, r, m = ops.mask(torch.from_numpy(z["noise_t"]).to(DEV), torch.from_numpy(z["noise_l"]).to(DEV), 3, 6)
+    assert hashlib.sha1(k.cpu().numpy().tobytes()).hexdigest()[:16] == "5ee5fac47baaef6e"
+    assert hashlib.sha1(r.cpu().numpy().tobytes()).hexdigest()[:16] == "466597abc0b24641"
+    assert torch.equal(k.cpu(), torch.from_numpy(z["large_ids_keep"]))
+    assert torch.equal(m.cpu(), torch.from_numpy(z["large_mask"]))
+
+
+def test_mask_empty_batch(ops):
+    k, r, m = ops.mask(torch.empty(0, 4, device=DEV), torch.empty(0, 9, device=DEV), 3, 6)
+    assert k.shape == (0, 18) and r.shape == (0, 36)
+
+
+# ---------------------------------------------------------------- GEMM epilogues
+GEMM_SHAPES = [(1000, 768, 256), (256, 256, 256), (130, 64, 64), (777, 192, 64), (512, 80, 64), (300, 256, 1376),
+               (300, 64, 352), (129, 256, 768), (1, 128, 128), (2048, 144, 144), (640, 256, 80)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1])
+def test_gemm_bias(ops, M, N, K, epi):
+    A, B = _rand_bf16(M, K, seed=1), _rand_bf16(N, K, scale=0.05, seed=2)
+    bias = torch.randn(N, device=DEV)
+    ref = A.float() @ B.float().t() + bias
+    tc = ops.gemm(A, B, epi, bias=bias)["out"]
+    ck = ops.gemm(A, B, epi, bias=bias, impl=ops.IMPL_SIMT)["out"]
+    tol = TOL_BF16 if epi == 0 else TOL_F32
+    assert rel_err(ck.float(), ref) < tol
+    assert rel_err(tc.float(), ref) < tol
+    nobias = ops.gemm(A, B, epi)["out"]
+    assert rel_err(nobias.float(), ref - bias) < tol
+
+
+def test_gemm_strided_operands(ops):
+    """operands that are column slices of wider buffers (lda != K), K not a multiple of 64"""
+    M, N, K = 500, 176, 72
+    Abig, Bbig = _rand_bf16(M, 80, seed=3), _rand_bf16(N, 80, scale=0.1, seed=4)
+    A, B = Abig[:, :K], Bbig[:, :K]
+    ref = A.float() @ B.float().t()
+    assert rel_err(ops.gemm(A, B, 1)["out"], ref) < TOL_F32
+    assert rel_err(ops.gemm(A, B, 1, impl=ops.IMPL_SIMT)["out"], ref) < TOL_F32
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (300, 256, 688), (4096, 64, 176), (129, 128, 352), (77, 144, 144), (260, 64, 64)])
+@pytest.mark.parametrize("variant", ["plain", "resid2+scale", "no_ln"])
+def test_gemm_resid_layernorm(ops, M, N, K, variant):
+    A, B = _rand_bf16(M, K, seed=5), _rand_bf16(N, K, scale=0.05, seed=6)
+    bias = 0.1 * torch.randn(N, device=DEV)
+    resid = 6.0 * torch.randn(M, N, device=DEV)
+    gamma, beta = 1 + 0.1 * torch.randn(N, device=DEV), 0.1 * torch.randn(N, device=DEV)
+    kw = dict(bias=bias, resid=resid, gamma=gamma, beta=beta)
+    y = A.float() @ B.float().t() + bias
+    if variant == "resid2+scale":
+        Ktok, ll, G = 6, 3, 2          # spatial-mode row groups: rows -> (b, t)
+        Mpad = (M + Ktok - 1) // Ktok
+        scale = (torch.rand(Mpad * G, device=DEV) > 0.3).float() / 0.7
+        r2 = torch.randn(M, N, device=DEV)
+        kw.update(resid2=r2, rowscale=scale, rs_mode=1, rs_K=Ktok, rs_len_l=ll, rs_G=G)
+        rows = torch.arange(M, device=DEV)
+        s = scale[(rows // Ktok) * G + (rows % Ktok) // ll]
+        x = resid + s[:, None] * y + r2
+    else:
+        x = resid + y
+    if variant == "no_ln":
+        kw.update(gamma=None, beta=None)
+    for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
+        out = ops.gemm(A, B, ops.EPI_RESID_LN, impl=impl, **kw)
+        assert rel_err(out["x"], x) < TOL_F32, impl
+        if variant != "no_ln":
+            ln = F.layer_norm(x, (N,), gamma, beta, 1e-5)
+            assert rel_err(out["ln"].float(), ln) < TOL_BF16, impl
+            mean, var = x.mean(1), x.var(1, unbiased=False)
+            assert torch.allclose(out["stats"][:, 0], mean, atol=1e-4)
+            assert torch.allclose(out["stats"][:, 1], (var + 1e-5).rsqrt(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,d,H", [(1000, 256, 684), (300, 64, 172), (129, 128, 344), (50, 144, 384)])
+def test_gemm_swiglu_fwd_bwd(ops, M, d, H):
+    hp = (H + 15) // 16 * 16
+    x = _rand_bf16(M, d, seed=7)
+    w1, w3 = _rand_bf16(H, d, scale=0.08, seed=8), _rand_bf16(H, d, scale=0.08, seed=9)
+    b1, b3 = 0.1 * torch.randn(H, device=DEV), 0.1 * torch.randn(H, device=DEV)
+    W = ops.pack_interleaved(w1, w3, hp)
+    bias = ops.pack_interleaved(b1[:, None], b3[:, None], hp)[:, 0].contiguous()
+    a_ref = x.float() @ w1.float().t() + b1
+    b_ref = x.float() @ w3.float().t() + b3
+    idx = torch.arange(H, device=DEV)
+    ca, cb = (idx // 16) * 32 + idx % 16, (idx // 16) * 32 + 16 + idx % 16
+    outs = {}
+    for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
+        o = ops.gemm(x, W, ops.EPI_SWIGLU, impl=impl, bias=bias)
+        outs[impl] = o
+        assert rel_err(o["ab"][:, ca].float(), a_ref) < TOL_BF16
+        assert rel_err(o["ab"][:, cb].float(), b_ref) < TOL_BF16
+        a16, b16 = o["ab"][:, ca].float(), o["ab"][:, cb].float()
+        assert rel_err(o["g"][:, :H].float(), F.silu(a16) * b16) < TOL_BF16
+        if hp > H:
+            assert float(o["g"][:, H:].abs().max()) == 0.0
+    # backward of the gate: dg = dy @ W2 (N = hp columns), fused with d(silu(a)*b)
+    dy = _rand_bf16(M, d, scale=0.1, seed=10)
+    w2 = _rand_bf16(d, H, scale=0.08, seed=11)
+    w2t = torch.zeros(hp, d, dtype=torch.bfloat16, device=DEV)
+    w2t[:H] = w2.t()
+    ab = outs[ops.IMPL_TC]["ab"]
+    a16, b16 = ab[:, ca].float().requires_grad_(True), ab[:, cb].float().requires_grad_(True)
+    dg = dy.float() @ w2.float()
+    (F.silu(a16) * b16).backward(dg)
+    for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
+        o = ops.gemm(dy, w2t, ops.EPI_DSWIGLU, impl=impl, ab=ab)
+        assert rel_err(o["dab"][:, ca].float(), a16.grad) < TOL_BF16
+        assert rel_err(o["dab"][:, cb].float(), b16.grad) < TOL_BF16
+
+
+# ---------------------------------------------------------------- wgrad
+@pytest.mark.parametrize("Mred,Nout,Kin", [(5000, 256, 256), (1000, 768, 256), (4097, 64, 64), (3000, 256, 688), (999, 192, 64),
+                                           (2000, 64, 176), (63, 128, 128), (1, 64, 64), (8192, 144, 144)])
+def test_wgrad_plain(ops, Mred, Nout, Kin):
+    Y, X = _rand_bf16(Mred, Nout, scale=0.1, seed=12), _rand_bf16(Mred, Kin, seed=13)
+    cols = Kin - 4 if Kin == 688 else Kin
+    ref = Y.float().t() @ X.float()
+    bref = Y.float().sum(0)
+    for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
+        dst = torch.ones(Nout, cols, device=DEV)
+        b = torch.zeros(Nout, device=DEV)
+        ops.wgrad(Y, X, dst, impl=impl, bias0=b, cols_valid=cols)
+        assert rel_err(dst - 1.0, ref[:, :cols]) < 2e-4, impl          # accumulates on top of the existing value
+        assert rel_err(b, bref) < 2e-4, impl
+
+
+def test_wgrad_interleaved_and_row_clip(ops):
+    Mred, H, d = 3000, 172, 64
+    hp = 176
+    dab = _rand_bf16(Mred, 2 * hp, scale=0.1, seed=14)
+    X = _rand_bf16(Mred, d, seed=15)
+    idx = torch.arange(H, device=DEV)
+    ca, cb = (idx // 16) * 32 + idx % 16, (idx // 16) * 32 + 16 + idx % 16
+    for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
+        g1, g3 = torch.zeros(H, d, device=DEV), torch.zeros(H, d, device=DEV)
+        b1, b3 = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+        ops.wgrad(dab, X, g1, impl=impl, dst1=g3, row_map=1, rows_valid=H, bias0=b1, bias1=b3)
+        assert rel_err(g1, dab[:, ca].float().t() @ X.float()) < 2e-4
+        assert rel_err(g3, dab[:, cb].float().t() @ X.float()) < 2e-4
+        assert rel_err(b1, dab[:, ca].float().sum(0)) < 2e-4 and rel_err(b3, dab[:, cb].float().sum(0)) < 2e-4
+    # decoder_pred: 80 packed rows of which 72 exist
+    Y, X2 = _rand_bf16(2000, 80, scale=0.1, seed=16), _rand_bf16(2000, 64, seed=17)
+    for impl in (ops.IMPL_SIMT, ops.IMPL_TC):
+        dst = torch.zeros(72, 64, device=DEV)
+        ops.wgrad(Y, X2, dst, impl=impl, rows_valid=72)
+        assert rel_err(dst, (Y.float().t() @ X2.float())[:72]) < 2e-4
+
+
+# ---------------------------------------------------------------- attention
+def _attn_ref(qkv, n, D, heads, K, groups):
+    """groups: LongTensor [nseq, len] of row offsets inside a sample"""
+    hd = D // heads
+    q, k, v = qkv.float().reshape(n, K, 3, heads, hd).unbind(2)
+    out = torch.zeros(n, K, heads, hd, device=qkv.device)
+    for rows in groups:
+        qs, ks, vs = q[:, rows].transpose(1, 2), k[:, rows].transpose(1, 2), v[:, rows].transpose(1, 2)
+        att = torch.softmax(qs @ ks.transpose(-1, -2) * hd ** -0.5, -1)
+        out[:, rows] = (att @ vs).transpose(1, 2)
+    return out.reshape(n * K, D)
+
+
+@pytest.mark.parametrize("n,D,heads,lt,ll,kind", [
+    (37, 256, 16, 3, 6, "spatial"), (37, 256, 16, 3, 6, "spectral"), (37, 256, 16, 3, 6, "full"),
+    (20, 256, 16, 2, 9, "spatial"), (20, 256, 16, 2, 9, "spectral"), (300, 64, 8, 4, 9, "full"),
+    (9, 128, 8, 4, 9, "spatial"), (9, 128, 8, 4, 9, "spectral"), (5, 64, 4, 2, 4, "spectral"), (1, 64, 4, 4, 2, "spatial")])
+def test_attention_fwd_bwd(ops, n, D, heads, lt, ll, kind):
+    K = lt * ll
+    if kind == "spatial":
+        spec = (lt, ll, ll, 1); groups = [torch.arange(ll) + t * ll for t in range(lt)]
+    elif kind == "spectral":
+        spec = (ll, lt, 1, ll); groups = [torch.arange(lt) * ll + l for l in range(ll)]
+    else:
+        spec = (1, K, K, 1); groups = [torch.arange(K)]
+    groups = [g.to(DEV) for g in groups]
+    qkv = _rand_bf16(n * K, 3 * D, seed=18)
+    out, lse = ops.attention_forward(qkv, n, D, heads, K, *spec)
+    leaf = qkv.float().requires_grad_(True)
+    ref = _attn_ref(leaf, n, D, heads, K, groups)
+    assert rel_err(out.float(), ref) < TOL_BF16
+    dout = _rand_bf16(n * K, D, scale=0.1, seed=19)
+    ref.backward(dout.float())
+    dqkv = ops.attention_backward(qkv, out, lse, dout, n, D, heads, K, *spec)
+    assert rel_err(dqkv.float(), leaf.grad) < 2e-2   # bf16 O/dO inputs + bf16 output
