@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the HSIMAE pretraining hot path (BASELINE.json metric: pretrain patches/sec, 9x9 HSI, fwd+bwd).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+A "step" is what the reference's training loop does per batch (Model_Pretraining.py:96-106): forward,
+zero_grad, backward, AdamW step -- on the HSIMAE-Large config (Model_Pretraining.py:121-131), mask ratio 0.5,
+batch 4096 synthetic 9x9x32 patches per GPU (BASELINE.json configs[1]); weak scaling over GPUs.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LARGE = dict(img_size=9, patch_size=3, in_chans=1, bands=32, b_patch_size=8, embed_dim=256, depth=12, num_heads=16, s_depth=9,
+             decoder_embed_dim=64, decoder_depth=8, decoder_num_heads=8, norm_pix_loss=True, trunc_init=True)
+FLOP_PER_PATCH = 1.893e9          # algorithmic fwd+bwd FLOP / patch, Large, mask 0.5
+CUBE = 32 * 9 * 9
+METRIC = "pretrain patches/sec (9x9 HSI, fwd+bwd)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_step_fn(batch: int):
+    """the reference algorithm (oracle port) as one training step on the host cores"""
+    from oracle import hsimae_oracle as O
+    geo = O.Geometry()
+    torch.manual_seed(42); random.seed(42)
+    sd = O.make_state(geo, seed=42)
+    leaves = {k: v.clone().requires_grad_(k not in O.FROZEN) for k, v in sd.items()}
+    no_decay = ("bias", "norm")
+    groups = [{"params": [p for n, p in leaves.items() if p.requires_grad and not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
+              {"params": [p for n, p in leaves.items() if p.requires_grad and any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    x = torch.randn(batch, 1, 32, 9, 9)
+
+    def step():
+        lt, ll = O.choose_visible_shape(geo.T, geo.L, 0.5)
+        out = O.pretrain_forward(leaves, x, geo, torch.rand(batch, geo.T), torch.rand(batch, geo.L), lt, ll)
+        opt.zero_grad()
+        out["loss"].backward()
+        opt.step()
+        return float(out["loss"])
+    return step
+
+
+def run_cpu(steps: int, warmup: int, batch: int = 64, budget_s: float = 1e9):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter(); done = 0
+    for _ in range(steps):
+        step(); done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=batch * done / dt, ms_per_step=1e3 * dt / done, cores=cores, steps=done, batch=batch)
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_cpu(args.steps, max(args.warmup, 1), 64, budget_s=240.0)
+    sample = f"HSIMAE-Large fwd+bwd+AdamW, batch {r['batch']} synthetic patches x {r['steps']} steps, fp32, {r['cores']} torch threads"
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "patches/s", "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "HSIMAE-Large pretraining step (fwd+bwd+AdamW), mask 0.5, 9x9x32 patches; CPU sample batch 64"},
+            "cpu_baseline": {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- dominant-kernel roofline
+def time_events(fn, iters: int):
+    """average device time of one launch: `iters` back-to-back launches between two events on the launching stream
+    (operands + outputs of every timed kernel are several times larger than the 126 MB L2, so nothing is served from cache)"""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / iters
+
+
+def dominant_kernel_roofline(batch: int, pk):
+    """Times the per-block GEMM kernels at the bench shapes (M = batch*18 encoder token rows) in isolation, picks the
+    class with the largest share of a step, and reports it against its binding roofline."""
+    from hsimae_b200 import ops
+    dev = "cuda"
+    M, D, H = batch * 18, 256, 688
+    bf = lambda *s: torch.randn(*s, device=dev).to(torch.bfloat16)
+    x, w13, wqkv, w2, wp = bf(M, D), bf(2 * H, D) * 0.05, bf(3 * D, D) * 0.05, bf(D, H) * 0.05, bf(D, D) * 0.05
+    g, resid = bf(M, H), torch.randn(M, D, device=dev)
+    gamma, beta = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    dab, dqkv = bf(M, 2 * H), bf(M, 3 * D)
+    gw13 = torch.zeros(684, D, device=dev); gw13b = torch.zeros(684, D, device=dev)
+    per_step = 21   # encoder blocks per direction
+    cands = {
+        "gemm_tc_kernel<SwiGLU> [M,256]x[256,1376]": (lambda: ops.gemm(x, w13, ops.EPI_SWIGLU), 2 * M * 2 * H * D,
+                                                      2 * (M * D + 2 * H * D + M * 2 * H + M * H), per_step),
+        "gemm_tc_kernel<ResidLN> [M,688]x[688,256]": (lambda: ops.gemm(g, w2, ops.EPI_RESID_LN, resid=resid, gamma=gamma, beta=beta),
+                                                      2 * M * D * H, 2 * (M * H + D * H + M * D) + 8 * M * D, per_step),
+        "gemm_tc_kernel<Bias> qkv [M,256]x[256,768]": (lambda: ops.gemm(x, wqkv, ops.EPI_BIAS_BF16), 2 * M * 3 * D * D,
+                                                       2 * (M * D + 3 * D * D + M * 3 * D), per_step),
+        "wgrad_tc_kernel dW13 [1376,M]x[M,256]": (lambda: ops.wgrad(dab, x, gw13, dst1=gw13b, row_map=1, rows_valid=684),
+                                                  2 * M * 2 * H * D, 2 * (M * 2 * H + M * D) + 4 * 2 * 684 * D, per_step),
+        "gemm_tc_kernel<Bias> dgrad [M,1376]x[1376,256]": (lambda: ops.gemm(dab, w13.t().contiguous(), ops.EPI_BIAS_BF16),
+                                                           2 * M * 2 * H * D, 2 * (M * 2 * H + 2 * H * D + M * D), per_step),
+    }
+    rows = {}
+    for name, (fn, flops, nbytes, count) in cands.items():
+        t = time_events(fn, 20)
+        rows[name] = dict(t=t, flops=flops, bytes=nbytes, count=count)
+    name = max(rows, key=lambda k: rows[k]["t"] * rows[k]["count"])
+    r = rows[name]
+    t_tensor, t_hbm = r["flops"] / (pk["tf"] * 1e12), r["bytes"] / (pk["hbm"] * 1e9)
+    if t_hbm >= t_tensor:
+        ach = r["bytes"] / r["t"] / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+    else:
+        ach = r["flops"] / r["t"] / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"]}
+    roof.update(kernel=name, us_per_launch=r["t"] * 1e6, traffic=None, peak_source=pk["src"],
+                algorithmic_bytes=r["bytes"], algorithmic_flops=r["flops"],
+                all_kernels={k: {"us": v["t"] * 1e6, "tflops": v["flops"] / v["t"] / 1e12, "gbs": v["bytes"] / v["t"] / 1e9}
+                             for k, v in rows.items()})
+    return roof
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="patches per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop (for ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_main(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import Models
+    from hsimae_b200 import _lib, dp
+
+    torch.manual_seed(42); random.seed(42)
+    model = Models.HSIMAE(**LARGE).to(dev)
+    model.train()
+    if world > 1:
+        dp.broadcast_parameters(model)
+        dp.attach(model)
+    no_decay = ["bias", "norm"]
+    groups = [{"params": [p for n, p in model.named_parameters() if not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
+              {"params": [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    torch.manual_seed(1000 + rank); random.seed(7)   # python RNG identical on all ranks (same visible shape), data differs
+    B = args.batch
+    pool = [torch.randn(B, 1, 32, 9, 9, device=dev) for _ in range(4)]
+    host_pool = [torch.randn(B, 1, 32, 9, 9).pin_memory() for _ in range(4)]
+    lib = _lib.load()
+
+    def step(x):
+        loss, _, _ = model(x, mask_ratio=0.5)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident inputs ("value")
+    for i in range(args.warmup):
+        step(pool[i % 4])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.hsimae_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if args.profile:
+        torch.cuda.profiler.start()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(pool[i % 4])
+    e1.record()
+    barrier()
+    if args.profile:
+        torch.cuda.profiler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = lib.hsimae_launch_count() - launches0
+    last_loss = float(loss.item())
+
+    # ---- end to end: pinned host batches, H2D every step (prefetched on a copy stream), loss read back every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty(B, 1, 32, 9, 9, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])
+            bufs[j].copy_(host_pool[i % 4], non_blocking=True)
+            ready[j].record(copy_stream)
+
+    def e2e_loop(n):
+        for c in consumed:
+            c.record()
+        prefetch(0)
+        tot = 0.0
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            l = step(bufs[i % 2])
+            consumed[i % 2].record()
+            tot += l.item()              # device -> host read of the step's result, every step
+        return tot
+
+    if args.no_e2e:
+        e2e_ms = wall_ms = float("nan")
+    else:
+        e2e_loop(2)
+        barrier()
+        e0.record()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps)
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    pk = peaks()
+    line = None
+    if rank == 0:
+        value = world * B / (ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "HSIMAE-Large pretraining step (fwd+bwd+AdamW as Model_Pretraining.py:96-106), mask 0.5, "
+                                       f"batch {B} synthetic 9x9x32 patches per GPU (BASELINE.json configs[1])",
+                           "global_batch": world * B, "parallelism": f"dp{world}",
+                           "l2": "4 rotating input batches; per-step activation working set (~15 GB) >> 126 MB L2",
+                           "optimizer": "torch.optim.AdamW (driver-owned, unchanged)"},
+                "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": B * CUBE * 4,
+                        "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps},
+                "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "loss": last_loss,
+                "clocks": clocks,
+                "step_tensor_frac": {"achieved_tflops": B * FLOP_PER_PATCH / (ms * 1e-3) / 1e12, "peak_tflops": pk["tf_sus"],
+                                     "frac": B * FLOP_PER_PATCH / (ms * 1e-3) / 1e12 / pk["tf_sus"], "peak": "sustained, " + pk["src"]}}
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and not args.no_roofline:
+        del pool, bufs
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        line["roofline"] = dominant_kernel_roofline(B, pk)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu(steps=10, warmup=2, batch=64, budget_s=20.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port",
+                                "sample": f"same step on the host: batch {r['batch']} x {r['steps']} steps, fp32 oracle port, "
+                                          f"{r['cores']} torch threads ({r['ms_per_step']:.0f} ms/step)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

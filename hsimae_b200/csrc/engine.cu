@@ -536,6 +536,7 @@ int hsimae_pack_params(hsimae_plan* p, const void* const* params, void* bf16_are
 
 int hsimae_mask(const float* noise_t, const float* noise_l, int32_t n, int32_t T, int32_t L, int32_t len_t, int32_t len_l,
                 int64_t* ids_keep, int64_t* ids_restore, float* mask, int32_t* ids_keep32, int32_t* ids_restore32, void* stream) {
+  if (n == 0) return kOk;
   HS_REQUIRE(noise_t && noise_l && ids_keep && ids_restore && mask, "mask: null argument");
   return launch_mask(noise_t, noise_l, n, T, L, len_t, len_l, ids_keep, ids_restore, mask, ids_keep32, ids_restore32, (cudaStream_t)stream);
 }

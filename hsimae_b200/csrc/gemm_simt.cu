@@ -50,8 +50,8 @@ template <int EPI>
 __global__ void __launch_bounds__(128)
 simt_epilogue_kernel(GemmArgs p, float* scratch, int ldc) {
   const int m = blockIdx.x * 128 + threadIdx.x;
-  const int mm = m < p.M ? m : p.M - 1;  // keep loads in bounds; stores are predicated on m < M
-  GmemAcc acc{scratch + (size_t)mm * ldc};
+  if (m >= p.M) return;  // the global-scratch accumulator needs no warp-collective access
+  GmemAcc acc{scratch + (size_t)m * ldc};
   run_epilogue<EPI>(p, acc, m, 0, p.N);
 }
 
