@@ -145,6 +145,6 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
                : "memory");
 }
 
-__device__ __forceinline__ float silu_f(float a) { return a / (1.0f + __expf(-a)); }
+__device__ __forceinline__ float silu_f(float a) { return __fdividef(a, 1.0f + __expf(-a)); }
 
 }  // namespace hsimae

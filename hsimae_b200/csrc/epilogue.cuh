@@ -18,6 +18,16 @@ __device__ __forceinline__ void load_f32_row(const float* p, float (&v)[W]) {
   }
 }
 
+// v[i] += vec[i], vec read with 128-bit (warp-uniform, L1-resident) loads
+template <int W>
+__device__ __forceinline__ void add_vec(const float* __restrict__ vec, float (&v)[W]) {
+#pragma unroll
+  for (int i = 0; i < W; i += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(vec + i));
+    v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+  }
+}
+
 template <int W>
 __device__ __forceinline__ void store_f32_row(float* p, const float (&v)[W]) {
 #pragma unroll
@@ -56,10 +66,7 @@ __device__ __forceinline__ void epi_bias_chunk(const GemmArgs& p, Acc& acc, int 
   acc.template load<W>(c, v);
   const int n = n0 + c;
   if (!valid || n >= p.N) return;
-  if (p.bias) {
-#pragma unroll
-    for (int i = 0; i < W; ++i) v[i] += __ldg(p.bias + n + i);
-  }
+  if (p.bias) add_vec<W>(p.bias + n, v);
   if (f32out) store_f32_row<W>(reinterpret_cast<float*>(p.out0) + (size_t)m * p.ld0 + n, v);
   else        store_bf16_row<W>(reinterpret_cast<__nv_bfloat16*>(p.out0) + (size_t)m * p.ld0 + n, v);
 }
@@ -73,11 +80,9 @@ __device__ __forceinline__ float epi_resid_chunk(const GemmArgs& p, Acc& acc, in
   if (valid) {
     float r[W];
     load_f32_row<W>(p.resid + (size_t)m * p.ldr + c, r);
+    if (p.bias) add_vec<W>(p.bias + c, v);
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-      float t = v[i] + (p.bias ? __ldg(p.bias + c + i) : 0.f);
-      v[i] = fmaf(s, t, r[i]);
-    }
+    for (int i = 0; i < W; ++i) v[i] = fmaf(s, v[i], r[i]);
     if (p.resid2) {
       load_f32_row<W>(p.resid2 + (size_t)m * p.ldr + c, r);
 #pragma unroll
@@ -107,7 +112,14 @@ __device__ __forceinline__ void epi_norm_chunk(const GemmArgs& p, Acc& acc, int 
   acc.template load<W>(c, v);
   if (!valid) return;
 #pragma unroll
-  for (int i = 0; i < W; ++i) v[i] = fmaf((v[i] - mean) * rstd, __ldg(p.gamma + c + i), __ldg(p.beta + c + i));
+  for (int i = 0; i < W; i += 4) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c + i));
+    v[i] = fmaf((v[i] - mean) * rstd, g.x, b.x);
+    v[i + 1] = fmaf((v[i + 1] - mean) * rstd, g.y, b.y);
+    v[i + 2] = fmaf((v[i + 2] - mean) * rstd, g.z, b.z);
+    v[i + 3] = fmaf((v[i + 3] - mean) * rstd, g.w, b.w);
+  }
   store_bf16_row<W>(reinterpret_cast<__nv_bfloat16*>(p.out1) + (size_t)m * p.ld1 + c, v);
 }
 
@@ -118,10 +130,7 @@ __device__ __forceinline__ void epi_swiglu_chunk(const GemmArgs& p, Acc& acc, in
   acc.template load<32>(c, v);
   const int n = n0 + c;
   if (!valid || n >= p.N) return;
-  if (p.bias) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + n + i);
-  }
+  if (p.bias) add_vec<32>(p.bias + n, v);
   store_bf16_row<32>(reinterpret_cast<__nv_bfloat16*>(p.out0) + (size_t)m * p.ld0 + n, v);
   float g[16];
 #pragma unroll
@@ -146,7 +155,7 @@ __device__ __forceinline__ void epi_dswiglu_chunk(const GemmArgs& p, Acc& acc, i
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float a = ab[i], b = ab[16 + i];
-    float sg = 1.0f / (1.0f + __expf(-a));
+    float sg = __fdividef(1.0f, 1.0f + __expf(-a));
     float si = a * sg;
     o[i] = dg[i] * b * (sg * (1.0f + a * (1.0f - sg)));
     o[16 + i] = dg[i] * si;

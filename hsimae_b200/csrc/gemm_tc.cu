@@ -184,28 +184,35 @@ __host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // 64 bf16 = one 128B swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kAccStride = 256;         // TMEM columns between the two accumulator stages
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;       // wgrad kernel: producer + MMA + 4 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
 
 // ---------------------------------------------------------------------------
 // forward / dgrad kernel
+//
+// These GEMMs are short in K (64..1376) and wide in output bytes, so the tile time
+// is set by the epilogue (global loads/stores + element-wise math), not by the
+// MMA.  The accumulator is therefore split into S TMEM stages (512/S columns
+// each) and every stage has its OWN group of four epilogue warps: up to S tiles
+// are being drained concurrently (S warps per scheduler hide each other's
+// TMEM / global latency) while the MMA warp fills the next free stage.
 // ---------------------------------------------------------------------------
-template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int EPI, int S>
+__global__ void __launch_bounds__(64 + 128 * S, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p,
                int block_n, int stages, int n_blks, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  constexpr uint32_t kAccStride = 512 / S;
 
   const uint32_t b_bytes = (uint32_t)block_n * 128u;
   const uint32_t stage_bytes = kATileBytes + b_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + S);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -246,8 +253,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc = make_idesc(block_n, false, false);
       int stage = 0; uint32_t phase = 0;
-      int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it % S;
+        const uint32_t aphase = (uint32_t)(it / S) & 1u;
         ptx::mbar_wait(tempty + as, aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * kAccStride;
@@ -266,23 +275,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         ptx::umma_commit(tfull + as);
-        as ^= 1; if (as == 0) aphase ^= 1u;
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;   // accumulator stage served by this warp's group
+    int it = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += S * gridDim.x, it += S) {
       const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
-      ptx::mbar_wait(tfull + as, aphase);
+      const uint32_t aphase = (uint32_t)(it / S) & 1u;
+      ptx::mbar_wait(tfull + grp, aphase);
       ptx::tc_fence_after();
-      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccStride};
+      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
       const int n0 = n_blk * block_n;
       int width = p.N - n0; if (width > block_n) width = block_n;
       run_epilogue<EPI>(p, acc, m_blk * kBlockM + q * 32 + lane, n0, width);
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty + as);
-      as ^= 1; if (as == 0) aphase ^= 1u;
+      ptx::mbar_arrive(tempty + grp);
     }
   }
 
@@ -295,7 +304,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // wgrad kernel: one (output tile, reduction split) per CTA
 // ---------------------------------------------------------------------------
 constexpr int kBoxBytes = 64 * 128;  // one {64 x 64} bf16 TMA box
+constexpr int kOnesBytes = 16 * 1024;  // all-ones B operand for the fused column sums
 
+// Bias gradients ride along: dbias[n] = sum_m Y[m,n] * 1 is one more MMA per K-step against an all-ones
+// B tile (N = 16) that lives in shared memory for the whole kernel -- a tile of ones is the same in every
+// swizzle/major layout -- accumulated in 16 extra TMEM columns.  Only the c_blk == 0 tiles do it.
 __global__ void __launch_bounds__(kGemmThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, WgradArgs p,
                 int bn, int stages, int tiles_c, int num_tiles, int kb_total, int kb_per_split,
@@ -307,7 +320,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t a_bytes = 2 * kBoxBytes;
   const uint32_t b_bytes = (uint32_t)(bn / 64) * kBoxBytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* ones = smem + (size_t)stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + kOnesBytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
@@ -320,7 +334,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const int kb0 = split * kb_per_split;
   int kb1 = kb0 + kb_per_split; if (kb1 > kb_total) kb1 = kb_total;
   const int nkb = kb1 - kb0;
+  const bool do_bias = p.bias0 != nullptr && c_blk == 0;
 
+  if (do_bias) {
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // bf16 1.0 x2
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core (async proxy)
+  }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmY);
     ptx::prefetch_tmap(&tmX);
@@ -328,7 +347,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     ptx::mbar_init(tfull, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -352,6 +371,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = make_idesc(bn, true, true);
+        const uint32_t idesc_ones = make_idesc(16, true, true);
+        const uint64_t ones_desc = make_smem_desc(ptx::smem_u32(ones), lbo, sbo);
         int stage = 0; uint32_t phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(full + stage, phase);
@@ -362,6 +383,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
             const uint64_t adesc = make_smem_desc(sa + k * kstep_bytes, lbo, sbo);
             const uint64_t bdesc = make_smem_desc(sa + a_bytes + k * kstep_bytes, lbo, sbo);
             ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (do_bias) ptx::umma_bf16(tmem_base + 256, adesc, ones_desc, idesc_ones, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(empty + stage);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -375,13 +397,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
       const int r = r_blk * kBlockM + q * 32 + lane;  // packed output row
       float* drow = nullptr;
+      float* brow = nullptr;
       if (r < p.Nout) {
         if (p.row_map == 0) {
-          if (r < p.rows_valid) drow = p.dst0 + (size_t)r * p.ld;
+          if (r < p.rows_valid) { drow = p.dst0 + (size_t)r * p.ld; brow = p.bias0 ? p.bias0 + r : nullptr; }
         } else {
           const int which = (r % (2 * kGate)) / kGate;
           const int h = (r / (2 * kGate)) * kGate + (r % kGate);
-          if (h < p.rows_valid) drow = (which ? p.dst1 : p.dst0) + (size_t)h * p.ld;
+          if (h < p.rows_valid) {
+            drow = (which ? p.dst1 : p.dst0) + (size_t)h * p.ld;
+            brow = p.bias0 ? (which ? p.bias1 : p.bias0) + h : nullptr;
+          }
         }
       }
       for (int c = 0; c < bn; c += 16) {
@@ -395,12 +421,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
             if (col + i < p.cols_valid) red_add_f32x4(drow + col + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
+      if (do_bias) {
+        float v[16];
+        ptx::tmem_ld16(tbase + 256, v);
+        ptx::tmem_ld_wait();
+        if (brow != nullptr) atomicAdd(brow, v[0]);
+      }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------------------
@@ -515,18 +547,26 @@ int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t
   return kOk;
 }
 
-template <int EPI>
-int launch_gemm(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, int block_n, int stages, int n_blks,
-                int num_tiles, size_t smem, cudaStream_t stream) {
+template <int EPI, int S>
+int launch_gemm_s(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, int block_n, int stages, int n_blks,
+                  int num_tiles, size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  gemm_tc_kernel<EPI><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, a, block_n, stages, n_blks, num_tiles);
+  gemm_tc_kernel<EPI, S><<<grid, 64 + 128 * S, smem, stream>>>(tmA, tmB, a, block_n, stages, n_blks, num_tiles);
   HS_CHECK_LAUNCH("gemm_tc_kernel");
   return kOk;
+}
+
+template <int EPI>
+int launch_gemm(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, int block_n, int stages, int n_blks,
+                int num_tiles, size_t smem, cudaStream_t stream) {
+  // as many accumulator stages (= epilogue warp groups) as fit in the 512 TMEM columns
+  if (block_n <= 128) return launch_gemm_s<EPI, 4>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+  return launch_gemm_s<EPI, 2>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
 }
 
 int env_int(const char* name, int dflt) {
@@ -551,13 +591,13 @@ int gemm_check_args(const GemmArgs& a, int epi) {
 }
 
 int pick_block_n(int N, int epi) {
-  if (epi == kEpiResidLN) return N;
-  if (N <= 256) return N;
-  // prefer the widest tile that wastes least on the tail
-  int best = 256, best_waste = 1 << 30;
-  for (int bn = 256; bn >= 128; bn -= 32) {
-    int waste = ceil_div(N, bn) * bn - N;
-    if (waste < best_waste) { best = bn; best_waste = waste; }
+  if (epi == kEpiResidLN) return N;   // LayerNorm needs the whole row in one tile
+  if (N <= 128) return N;
+  // epilogue-bound: four 128-column accumulator stages beat two 256-column ones unless the tail wastes too much
+  int best = 128, best_cost = 1 << 30;
+  for (int bn = 128; bn >= 64; bn -= 32) {
+    int cost = ceil_div(N, bn) * bn;
+    if (cost < best_cost) { best = bn; best_cost = cost; }
   }
   return best;
 }
@@ -627,9 +667,9 @@ int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
   const int kb_per = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, kb_per);
   const int stage_bytes = (2 + bn / 64) * kBoxBytes;
-  int stages = kSmemBudget / stage_bytes;
+  int stages = (kSmemBudget - kOnesBytes) / stage_bytes;
   if (stages > 8) stages = 8;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + kOnesBytes + 1024 + 256;
   CUtensorMap tmY, tmX;
   HS_TRY(get_tmap(a.Y, (uint64_t)a.Nout, (uint64_t)a.Mred, (uint64_t)a.ldy, 64, 64, &tmY));
   HS_TRY(get_tmap(a.X, (uint64_t)a.Kin, (uint64_t)a.Mred, (uint64_t)a.ldx, 64, 64, &tmX));
@@ -639,10 +679,15 @@ int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
   const uint32_t lbo = (uint32_t)env_int("HSIMAE_WGRAD_LBO", kBoxBytes);
   const uint32_t sbo = (uint32_t)env_int("HSIMAE_WGRAD_SBO", 1024);
   const uint32_t kstep = (uint32_t)env_int("HSIMAE_WGRAD_KSTEP", 2048);
-  wgrad_tc_kernel<<<num_tiles * splits, kGemmThreads, smem, stream>>>(tmY, tmX, a, bn, stages, tiles_c, num_tiles, kb_total,
+  // bias gradients are fused (ones-operand MMA); HSIMAE_WGRAD_FUSED_BIAS=0 selects the separate column-sum kernel (A/B debugging)
+  static const bool fused = env_int("HSIMAE_WGRAD_FUSED_BIAS", 1) != 0;
+  WgradArgs k = a;
+  if (!fused) { k.bias0 = nullptr; k.bias1 = nullptr; }
+  wgrad_tc_kernel<<<num_tiles * splits, kGemmThreads, smem, stream>>>(tmY, tmX, k, bn, stages, tiles_c, num_tiles, kb_total,
                                                                       kb_per, lbo, sbo, kstep);
   HS_CHECK_LAUNCH("wgrad_tc_kernel");
-  return launch_colsum(a, stream);
+  if (!fused) return launch_colsum(a, stream);
+  return kOk;
 }
 
 }  // namespace hsimae

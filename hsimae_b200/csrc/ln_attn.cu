@@ -69,12 +69,131 @@ ln_bwd_kernel(LnBwdArgs a) {
   }
 }
 
+// Vector variant for D = 32*VEC (VEC in {2,4,8}): each lane owns VEC contiguous elements (128-bit fp32 / 64..128-bit
+// bf16 accesses), two rows per warp iteration so that both rows' loads are in flight before the first reduction.
+template <int VEC> struct VecIO;
+template <> struct VecIO<8> {
+  static __device__ __forceinline__ void ldf(const float* p, float (&v)[8]) {
+    // coherent streaming loads: dx_in may alias dx_out (in-place update by the owning thread)
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void ldh(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = ld_stream_u4(p);
+    const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  static __device__ __forceinline__ void stf(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ void sth(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t; t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+template <> struct VecIO<4> {
+  static __device__ __forceinline__ void ldf(const float* p, float (&v)[4]) { const float4 a = __ldcs(reinterpret_cast<const float4*>(p)); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+  static __device__ __forceinline__ void ldh(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void stf(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+  static __device__ __forceinline__ void sth(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 t; t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+template <> struct VecIO<2> {
+  static __device__ __forceinline__ void ldf(const float* p, float (&v)[2]) { const float2 a = *reinterpret_cast<const float2*>(p); v[0] = a.x; v[1] = a.y; }
+  static __device__ __forceinline__ void ldh(const __nv_bfloat16* p, float (&v)[2]) { const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p)); v[0] = a.x; v[1] = a.y; }
+  static __device__ __forceinline__ void stf(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+  static __device__ __forceinline__ void sth(__nv_bfloat16* p, const float (&v)[2]) { *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]); }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+ln_bwd_vec_kernel(LnBwdArgs a) {
+  constexpr int D = 32 * VEC;
+  __shared__ float sg[8][D];
+  __shared__ float sb[8][D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e0 = lane * VEC;
+  float gam[VEC], dgam[VEC], dbet[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { gam[j] = a.gamma[e0 + j]; dgam[j] = 0.f; dbet[j] = 0.f; }
+  const float invD = 1.0f / D;
+  const int stride = gridDim.x * 8 * 2;
+  for (int m0 = (blockIdx.x * 8 + warp) * 2; m0 < a.M; m0 += stride) {
+    float xv[2][VEC], dyv[2][VEC], din[2][VEC], mean[2], rstd[2];
+    bool ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int m = m0 + r;
+      ok[r] = m < a.M;
+      if (ok[r]) {
+        const size_t off = (size_t)m * D + e0;
+        VecIO<VEC>::ldf(a.x + off, xv[r]);
+        VecIO<VEC>::ldh(a.dy + off, dyv[r]);
+        if (a.dx_in) VecIO<VEC>::ldf(a.dx_in + off, din[r]);
+        const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * (size_t)m);
+        mean[r] = st.x; rstd[r] = st.y;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (!ok[r]) continue;   // warp-uniform
+      const int m = m0 + r;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        xv[r][j] = (xv[r][j] - mean[r]) * rstd[r];
+        const float t = dyv[r][j] * gam[j];
+        s1 += t; s2 = fmaf(t, xv[r][j], s2);
+        dgam[j] = fmaf(dyv[r][j], xv[r][j], dgam[j]);
+        dbet[j] += dyv[r][j];
+      }
+      s1 = warp_sum(s1) * invD;
+      s2 = warp_sum(s2) * invD;
+      float o[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        o[j] = rstd[r] * (dyv[r][j] * gam[j] - s1 - xv[r][j] * s2);
+        if (a.dx_in) o[j] += din[r][j];
+      }
+      const size_t off = (size_t)m * D + e0;
+      VecIO<VEC>::stf(a.dx_out + off, o);
+      if (a.dxb) {
+        const float sc = row_scale(a.rs, m);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] *= sc;
+        VecIO<VEC>::sth(a.dxb + off, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { sg[warp][e0 + j] = dgam[j]; sb[warp][e0 + j] = dbet[j]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { g += sg[w][i]; b += sb[w][i]; }
+    if (a.dgamma) atomicAdd(a.dgamma + i, g);
+    if (a.dbeta) atomicAdd(a.dbeta + i, b);
+  }
+}
+
 int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t stream) {
   HS_REQUIRE(a.D <= 32 * kLnMaxPerLane, "ln_bwd: D=%d > %d unsupported", a.D, 32 * kLnMaxPerLane);
   if (a.M == 0) return kOk;
-  int grid = ceil_div(a.M, 8);
-  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
-  ln_bwd_kernel<<<grid, 256, 0, stream>>>(a);
+  int grid = ceil_div(a.M, 16);
+  if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+  // dx_in == dx_out (in-place) is fine: every element is read and written by the same thread
+  if (a.D == 256) ln_bwd_vec_kernel<8><<<grid, 256, 0, stream>>>(a);
+  else if (a.D == 128) ln_bwd_vec_kernel<4><<<grid, 256, 0, stream>>>(a);
+  else if (a.D == 64) ln_bwd_vec_kernel<2><<<grid, 256, 0, stream>>>(a);
+  else ln_bwd_kernel<<<grid, 256, 0, stream>>>(a);
   HS_CHECK_LAUNCH("ln_bwd_kernel");
   return kOk;
 }

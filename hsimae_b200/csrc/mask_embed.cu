@@ -160,6 +160,82 @@ embed_fwd_kernel(EmbedArgs a) {
   }
 }
 
+// Specialisation for a compile-time patch geometry (the reference's 8x3x3 patches of a 9x9 cube): the (u,p,q)
+// loops unroll into immediate shared-memory offsets, so the inner loop is one broadcast LDS + one FFMA per MAC.
+template <int U, int P, int IMG, int TK>
+__global__ void __launch_bounds__(kEmbedThreads)
+embed_fwd_fixed_kernel(EmbedArgs a) {
+  extern __shared__ float sm[];
+  const PatchGeom g = a.g;
+  constexpr int PK = U * P * P;
+  const int D = a.D, K = a.K;
+  float* sW = sm;                         // [PK][D]
+  float* sCube = sW + (size_t)PK * D;     // [cube]
+  float* sX = sCube + g.cube;             // [K][D]
+  int* sBase = reinterpret_cast<int*>(sX + (size_t)K * D);  // [K] cube offset of each kept token
+  int* sTok = sBase + K;                  // [K]
+  for (int i = threadIdx.x; i < PK * D; i += blockDim.x) {
+    const int d = i / PK, j = i - d * PK;
+    sW[(size_t)j * D + d] = a.W[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
+    for (int i = threadIdx.x; i < g.cube / 4; i += blockDim.x) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int tok = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
+      sTok[i] = tok;
+      sBase[i] = cube_index(g, tok, 0);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float b = a.bias ? a.bias[d] : 0.f;
+      for (int k0 = 0; k0 < K; k0 += TK) {
+        float acc[TK];
+        const float* base[TK];
+#pragma unroll
+        for (int k = 0; k < TK; ++k) { acc[k] = 0.f; base[k] = sCube + sBase[k0 + k < K ? k0 + k : K - 1]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int pp = 0; pp < P; ++pp)
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+              const float w = sW[(size_t)((u * P + pp) * P + q) * D + d];
+#pragma unroll
+              for (int k = 0; k < TK; ++k) acc[k] = fmaf(base[k][(u * IMG + pp) * IMG + q], w, acc[k]);
+            }
+#pragma unroll
+        for (int k = 0; k < TK; ++k)
+          if (k0 + k < K) sX[(size_t)(k0 + k) * D + d] = acc[k] + b + __ldg(a.pos + (size_t)sTok[k0 + k] * D + d);
+      }
+    }
+    __syncthreads();
+    for (int k = warp; k < K; k += nwarps) {
+      const float* xr = sX + (size_t)k * D;
+      const size_t m = (size_t)n * K + k;
+      float s = 0.f;
+      for (int i = lane; i < D; i += 32) s += xr[i];
+      const float mean = warp_sum(s) / D;
+      float sq = 0.f;
+      for (int i = lane; i < D; i += 32) { const float dv = xr[i] - mean; sq = fmaf(dv, dv, sq); }
+      const float rstd = rsqrtf(warp_sum(sq) / D + a.eps);
+      for (int i = lane; i < D; i += 32) {
+        const float v = xr[i];
+        a.x[m * D + i] = v;
+        const float xh = (v - mean) * rstd;
+        if (a.ln_a) a.ln_a[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_a[i], a.beta_a[i]));
+        if (a.ln_b) a.ln_b[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_b[i], a.beta_b[i]));
+      }
+      if (lane == 0) {
+        if (a.stats_a) { a.stats_a[2 * m] = mean; a.stats_a[2 * m + 1] = rstd; }
+        if (a.stats_b) { a.stats_b[2 * m] = mean; a.stats_b[2 * m + 1] = rstd; }
+      }
+    }
+  }
+}
+
 static size_t embed_fwd_smem(const EmbedArgs& a) {
   return ((size_t)a.g.PK * a.D + a.g.cube + (size_t)a.K * a.D) * sizeof(float) + ((size_t)a.K * a.g.PK + a.K) * sizeof(int);
 }
@@ -170,9 +246,14 @@ int launch_embed_fwd(const EmbedArgs& a, cudaStream_t stream) {
   if (a.N == 0) return kOk;
   const size_t smem = embed_fwd_smem(a);
   HS_REQUIRE(smem <= 227 * 1024, "embed: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
-  HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = a.N < kNumSMs ? a.N : kNumSMs;
-  embed_fwd_kernel<<<grid, kEmbedThreads, smem, stream>>>(a);
+  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_fixed_kernel<8, 3, 9, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    embed_fwd_fixed_kernel<8, 3, 9, 9><<<grid, kEmbedThreads, smem, stream>>>(a);
+  } else {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    embed_fwd_kernel<<<grid, kEmbedThreads, smem, stream>>>(a);
+  }
   HS_CHECK_LAUNCH("embed_fwd_kernel");
   return kOk;
 }
@@ -233,13 +314,61 @@ embed_bwd_kernel(EmbedBwdArgs a) {
   }
 }
 
+template <int U, int P, int IMG>
+__global__ void __launch_bounds__(256)
+embed_bwd_fixed_kernel(EmbedBwdArgs a) {
+  extern __shared__ float sm[];
+  const PatchGeom g = a.g;
+  constexpr int PK = U * P * P;
+  const int D = a.D, K = a.K;
+  float* sCube = sm;
+  int* sBase = reinterpret_cast<int*>(sCube + g.cube);
+  for (int d0 = 0; d0 < D; d0 += blockDim.x) {
+    const int d = d0 + threadIdx.x;
+    float acc[PK];
+#pragma unroll
+    for (int j = 0; j < PK; ++j) acc[j] = 0.f;
+    float bsum = 0.f;
+    for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+      __syncthreads();
+      const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
+      for (int i = threadIdx.x; i < g.cube / 4; i += blockDim.x) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+      for (int i = threadIdx.x; i < K; i += blockDim.x) sBase[i] = cube_index(g, a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i, 0);
+      __syncthreads();
+      if (d < D) {
+        for (int k = 0; k < K; ++k) {
+          const size_t m = (size_t)n * K + k;
+          float gv = a.dx_a[m * D + d];
+          if (a.dx_b) gv += a.dx_b[m * D + d];
+          bsum += gv;
+          const float* base = sCube + sBase[k];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp)
+#pragma unroll
+              for (int q = 0; q < P; ++q) acc[(u * P + pp) * P + q] = fmaf(gv, base[(u * IMG + pp) * IMG + q], acc[(u * P + pp) * P + q]);
+        }
+      }
+    }
+    if (d < D) {
+#pragma unroll
+      for (int j = 0; j < PK; ++j) atomicAdd(a.dW + (size_t)d * PK + j, acc[j]);
+      if (a.dbias) atomicAdd(a.dbias + d, bsum);
+    }
+  }
+}
+
 int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream) {
   HS_REQUIRE(a.g.PK <= kMaxPK, "embed_bwd: patch of %d elements unsupported (max %d)", a.g.PK, kMaxPK);
   if (a.N == 0) return kOk;
   const size_t smem = (size_t)a.g.cube * sizeof(float) + ((size_t)a.K * a.g.PK + a.K) * sizeof(int);
   HS_REQUIRE(smem <= 227 * 1024, "embed_bwd: needs %zu bytes of shared memory", smem);
   const int grid = a.N < kNumSMs ? a.N : kNumSMs;
-  if (a.g.PK <= 72) {
+  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_fixed_kernel<8, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    embed_bwd_fixed_kernel<8, 3, 9><<<grid, 256, smem, stream>>>(a);
+  } else if (a.g.PK <= 72) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     embed_bwd_kernel<72><<<grid, 256, smem, stream>>>(a);
   } else {
