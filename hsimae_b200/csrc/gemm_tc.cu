@@ -17,6 +17,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstdlib>
+#include <type_traits>
 #include "epilogue.cuh"
 
 namespace hsimae {
@@ -63,6 +64,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -152,6 +164,202 @@ struct TmemAcc {
 };
 
 // ---------------------------------------------------------------------------
+// Tensor-core epilogues with coalesced output: every epilogue warp owns 32
+// accumulator rows; it assembles [32 rows x 128 B] output boxes in its own
+// swizzled shared-memory staging buffers and hands them to the TMA store unit
+// (one elected lane), which also clips the M / N tails.  Same arithmetic as
+// the row-wise reference epilogues in epilogue.cuh (the checker path).
+// ---------------------------------------------------------------------------
+constexpr int kStageBufBytes = 32 * 128;   // one box
+constexpr int kStageBufsPerWarp = 2;
+
+struct Stager {
+  uint32_t base;     // smem address of this warp's two 4 KB buffers (1024-byte aligned)
+  int lane;
+  bool pending;      // a committed store may still be reading the buffers
+  int cur = 0;       // buffer being filled when the two are used in strict alternation
+  // wait until the TMA unit has finished reading every box this warp handed over
+  __device__ __forceinline__ void acquire() {
+    if (pending) {
+      if (lane == 0) ptx::bulk_wait_read0();
+      __syncwarp();
+      pending = false;
+    }
+  }
+  // strict alternation: the most recent store read the OTHER buffer and may stay in flight
+  __device__ __forceinline__ int begin_box() {
+    if (pending) {
+      if (lane == 0) ptx::bulk_wait_read1();
+      __syncwarp();
+    }
+    return cur;
+  }
+  __device__ __forceinline__ void end_box(const CUtensorMap* tm, int col, int row) { flush(cur, tm, col, row); cur ^= 1; }
+  // 16-byte piece j (0..7) of this lane's 128-byte box row; 128B-swizzle: piece index XOR (row & 7)
+  __device__ __forceinline__ void put(int b, int j, uint4 v) {
+    ptx::st_shared_v4(base + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v);
+  }
+  __device__ __forceinline__ void flush(int b, const CUtensorMap* tm, int col, int row) {
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) { ptx::tma_store_2d(tm, base + (uint32_t)b * kStageBufBytes, col, row); ptx::bulk_commit(); }
+    pending = true;
+  }
+};
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  uint4 t;
+  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+  return t;
+}
+__device__ __forceinline__ uint4 pack4_f32(const float* v) {
+  return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+}
+
+// A staged box is only safe to refill after the previous store from it was read; with two buffers used
+// alternately the wait (issued after the chunk's math) is almost always already satisfied.
+template <int W, bool F32>
+__device__ __forceinline__ void tc_bias_chunk(const GemmArgs& p, TmemAcc& acc, Stager& st, const CUtensorMap* tmO, int m0, int n0,
+                                              int c, int width) {
+  float v[W];
+  acc.template load<W>(c, v);
+  if (p.bias) add_vec<W>(p.bias + n0 + c, v);
+  if constexpr (F32) {
+    const int b = st.begin_box();
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) st.put(b, i, pack4_f32(v + 4 * i));
+    st.end_box(tmO, n0 + c, m0);
+  } else {
+    const int b = (c & 63) == 0 ? st.begin_box() : st.cur;
+    const int j0 = (c & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < W / 8; ++i) st.put(b, j0 + i, pack8_bf16(v + 8 * i));
+    if (((c + W) & 63) == 0 || c + W >= width) st.end_box(tmO, n0 + (c & ~63), m0);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Stager& st, const CUtensorMap* tmO0,
+                                            const CUtensorMap* tmO1, int m0, int lane, int n0, int width) {
+  const int m = m0 + lane;
+  const bool valid = m < p.M;
+  if constexpr (EPI == kEpiBiasBf16 || EPI == kEpiBiasF32) {
+    constexpr bool F32 = EPI == kEpiBiasF32;
+    int c = 0;
+    for (; c + 32 <= width; c += 32) tc_bias_chunk<32, F32>(p, acc, st, tmO0, m0, n0, c, width);
+    for (; c + 16 <= width; c += 16) tc_bias_chunk<16, F32>(p, acc, st, tmO0, m0, n0, c, width);
+  } else if constexpr (EPI == kEpiSwiGLU) {
+    // tile of packed (a|b interleaved by 16) columns; buffer 0: a|b boxes (64 packed columns), buffer 1: the gate box
+    for (int c = 0; c + 32 <= width; c += 32) {
+      float v[32];
+      acc.template load<32>(c, v);
+      if (p.bias) add_vec<32>(p.bias + n0 + c, v);
+      float g[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = bf16_round(v[i]), b = bf16_round(v[16 + i]);   // gate on what backward will re-read
+        g[i] = silu_f(a) * b;
+      }
+      if ((c & 63) == 0) st.acquire();
+      const int j0 = (c & 63) >> 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st.put(0, j0 + i, pack8_bf16(v + 8 * i));
+      st.put(1, (c >> 5) * 2, pack8_bf16(g));
+      st.put(1, (c >> 5) * 2 + 1, pack8_bf16(g + 8));
+      if (((c + 32) & 63) == 0 || c + 32 >= width) st.flush(0, tmO0, n0 + (c & ~63), m0);
+    }
+    st.flush(1, tmO1, n0 >> 1, m0);
+  } else if constexpr (EPI == kEpiDSwiGLU) {
+    // tile of hidden columns; every 16 of them become 32 packed output columns
+    for (int c = 0; c + 16 <= width; c += 16) {
+      float dg[16];
+      acc.template load<16>(c, dg);
+      float ab[32], o[32];
+      if (valid) load_bf16_row<32>(p.ab + (size_t)m * p.ldab + 2 * (n0 + c), ab);
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ab[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = ab[i], b = ab[16 + i];
+        const float sg = __fdividef(1.0f, 1.0f + __expf(-a));
+        o[i] = dg[i] * b * (sg * (1.0f + a * (1.0f - sg)));
+        o[16 + i] = dg[i] * (a * sg);
+      }
+      const int b = (c & 31) == 0 ? st.begin_box() : st.cur;
+      const int j0 = ((c & 31) >> 4) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st.put(b, j0 + i, pack8_bf16(o + 8 * i));
+      if (((c + 16) & 31) == 0 || c + 16 >= width) st.end_box(tmO0, 2 * (n0 + (c & ~31)), m0);
+    }
+  } else if constexpr (EPI == kEpiResidLN) {
+    // the tile spans the whole row (n0 == 0, width == N)
+    const bool ln = p.gamma != nullptr;
+    const float s = valid ? row_scale(p.rs, m) : 1.0f;
+    float sum = 0.f;
+    auto pass1 = [&](auto wtag, int c) {
+      constexpr int W = decltype(wtag)::value;
+      float v[W];
+      acc.template load<W>(c, v);
+      if (valid) {
+        float r[W];
+        load_f32_row<W>(p.resid + (size_t)m * p.ldr + c, r);
+        if (p.bias) add_vec<W>(p.bias + c, v);
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] = fmaf(s, v[i], r[i]);
+        if (p.resid2) {
+          load_f32_row<W>(p.resid2 + (size_t)m * p.ldr + c, r);
+#pragma unroll
+          for (int i = 0; i < W; ++i) v[i] += r[i];
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i) sum += v[i];
+      }
+      if (ln) acc.template store<W>(c, v);
+      const int b = st.begin_box();
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) st.put(b, i, pack4_f32(v + 4 * i));
+      st.end_box(tmO0, c, m0);
+    };
+    int c = 0;
+    for (; c + 32 <= width; c += 32) pass1(std::integral_constant<int, 32>{}, c);
+    for (; c + 16 <= width; c += 16) pass1(std::integral_constant<int, 16>{}, c);
+    if (ln) {
+      acc.fence_store();
+      const float inv = 1.0f / (float)width;
+      const float mean = sum * inv;
+      float sq = 0.f;
+      for (c = 0; c + 32 <= width; c += 32) sq += epi_sqdev_chunk<32>(acc, c, mean);
+      for (; c + 16 <= width; c += 16) sq += epi_sqdev_chunk<16>(acc, c, mean);
+      const float rstd = rsqrtf(sq * inv + p.ln_eps);
+      auto pass3 = [&](auto wtag, int c) {
+        constexpr int W = decltype(wtag)::value;
+        float v[W];
+        acc.template load<W>(c, v);
+#pragma unroll
+        for (int i = 0; i < W; i += 4) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c + i));
+          const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c + i));
+          v[i] = fmaf((v[i] - mean) * rstd, g.x, be.x);
+          v[i + 1] = fmaf((v[i + 1] - mean) * rstd, g.y, be.y);
+          v[i + 2] = fmaf((v[i + 2] - mean) * rstd, g.z, be.z);
+          v[i + 3] = fmaf((v[i + 3] - mean) * rstd, g.w, be.w);
+        }
+        const int b = (c & 63) == 0 ? st.begin_box() : st.cur;
+        const int j0 = (c & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < W / 8; ++i) st.put(b, j0 + i, pack8_bf16(v + 8 * i));
+        if (((c + W) & 63) == 0 || c + W >= width) st.end_box(tmO1, c & ~63, m0);
+      };
+      for (c = 0; c + 32 <= width; c += 32) pass3(std::integral_constant<int, 32>{}, c);
+      for (; c + 16 <= width; c += 16) pass3(std::integral_constant<int, 16>{}, c);
+      if (valid && p.stats) *reinterpret_cast<float2*>(p.stats + 2 * (size_t)m) = make_float2(mean, rstd);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // descriptors
 // ---------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
@@ -199,16 +407,19 @@ constexpr int kSmemBudget = 200 * 1024;
 // ---------------------------------------------------------------------------
 template <int EPI, int S>
 __global__ void __launch_bounds__(64 + 128 * S, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, GemmArgs p,
                int block_n, int stages, int n_blks, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   constexpr uint32_t kAccStride = 512 / S;
+  constexpr uint32_t kStagingBytes = 4 * S * kStageBufsPerWarp * kStageBufBytes;
 
   const uint32_t b_bytes = (uint32_t)block_n * 128u;
   const uint32_t stage_bytes = kATileBytes + b_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)stages * stage_bytes;   // 1024-byte aligned (stage_bytes is a multiple of 1024)
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
   uint64_t* tempty = tfull + S;
@@ -221,6 +432,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmO0);
+    ptx::prefetch_tmap(&tmO1);
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
     for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
     ptx::fence_barrier_init();
@@ -280,6 +493,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;   // accumulator stage served by this warp's group
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (kStageBufsPerWarp * kStageBufBytes), lane, false, 0};
     int it = grp;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += S * gridDim.x, it += S) {
       const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
@@ -289,10 +503,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
       const int n0 = n_blk * block_n;
       int width = p.N - n0; if (width > block_n) width = block_n;
-      run_epilogue<EPI>(p, acc, m_blk * kBlockM + q * 32 + lane, n0, width);
+      tc_epilogue<EPI>(p, acc, st, &tmO0, &tmO1, m_blk * kBlockM + q * 32, lane, n0, width);
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty + grp);
     }
+    st.acquire();   // the staging buffers must outlive every store that reads them
   }
 
   ptx::tc_fence_before();
@@ -495,16 +710,16 @@ EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; uint64_t d0, d1, pitch; uint32_t b0, b1;
+  const void* ptr; uint64_t d0, d1, pitch; uint32_t b0, b1, esz;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && pitch == o.pitch && b0 == o.b0 && b1 == o.b1;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && pitch == o.pitch && b0 == o.b0 && b1 == o.b1 && esz == o.esz;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&h](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.d0); mix(k.d1); mix(k.pitch); mix(k.b0); mix(k.b1);
+    mix(k.d0); mix(k.d1); mix(k.pitch); mix(k.b0); mix(k.b1); mix(k.esz);
     return h;
   }
 };
@@ -512,9 +727,10 @@ struct MapKeyHash {
 std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2-D bf16 tensor, dim0 contiguous (d0 elements), d1 rows of `pitch` elements, box {b0, b1}, 128B swizzle.
-int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t b0, uint32_t b1, CUtensorMap* out) {
-  MapKey key{ptr, d0, d1, pitch, b0, b1};
+// 2-D tensor of bf16 (esz 2) or fp32 (esz 4), dim0 contiguous (d0 elements), d1 rows of `pitch` elements,
+// box {b0, b1} with b0 * esz == 128 bytes, 128B swizzle.
+int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t b0, uint32_t b1, CUtensorMap* out, uint32_t esz = 2) {
+  MapKey key{ptr, d0, d1, pitch, b0, b1, esz};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -523,14 +739,14 @@ int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return kCudaError; }
   HS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand %p is not 16-byte aligned", ptr);
-  HS_REQUIRE((pitch * 2) % 16 == 0, "TMA operand pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)pitch);
-  HS_REQUIRE(b0 * 2 == 128 && b1 <= 256, "bad TMA box {%u,%u}", b0, b1);
+  HS_REQUIRE((pitch * esz) % 16 == 0, "TMA operand pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)pitch);
+  HS_REQUIRE(b0 * esz == 128 && b1 <= 256, "bad TMA box {%u,%u}", b0, b1);
   cuuint64_t dims[2] = {d0, d1};
-  cuuint64_t strides[1] = {pitch * 2};
+  cuuint64_t strides[1] = {pitch * esz};
   cuuint32_t box[2] = {b0, b1};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(&m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -547,26 +763,36 @@ int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t
   return kOk;
 }
 
+constexpr int kSmemMax = 227 * 1024;
+
 template <int EPI, int S>
-int launch_gemm_s(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, int block_n, int stages, int n_blks,
-                  int num_tiles, size_t smem, cudaStream_t stream) {
+int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int num_tiles, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
+  // shared memory: [operand pipeline stages][epilogue staging boxes][barriers]; as many stages as fit
+  const int staging = 4 * S * kStageBufsPerWarp * kStageBufBytes;
+  const int stage_bytes = kATileBytes + block_n * 128;
+  const int num_kb = ceil_div(a.K, kBlockK);
+  int stages = (kSmemMax - staging - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > 2 * num_kb) stages = 2 * num_kb;
+  if (stages < 2) stages = 2;
+  const size_t smem = (size_t)stages * stage_bytes + staging + 1024 + 512;
+  HS_REQUIRE(smem <= (size_t)kSmemMax, "gemm: tile N=%d needs %zu bytes of shared memory", block_n, smem);
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  gemm_tc_kernel<EPI, S><<<grid, 64 + 128 * S, smem, stream>>>(tmA, tmB, a, block_n, stages, n_blks, num_tiles);
+  gemm_tc_kernel<EPI, S><<<grid, 64 + 128 * S, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], a, block_n, stages, n_blks, num_tiles);
   HS_CHECK_LAUNCH("gemm_tc_kernel");
   return kOk;
 }
 
 template <int EPI>
-int launch_gemm(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, int block_n, int stages, int n_blks,
-                int num_tiles, size_t smem, cudaStream_t stream) {
+int launch_gemm(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int num_tiles, cudaStream_t stream) {
   // as many accumulator stages (= epilogue warp groups) as fit in the 512 TMEM columns
-  if (block_n <= 128) return launch_gemm_s<EPI, 4>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
-  return launch_gemm_s<EPI, 2>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+  if (block_n <= 128) return launch_gemm_s<EPI, 4>(a, tm, block_n, n_blks, num_tiles, stream);
+  return launch_gemm_s<EPI, 2>(a, tm, block_n, n_blks, num_tiles, stream);
 }
 
 int env_int(const char* name, int dflt) {
@@ -590,39 +816,49 @@ int gemm_check_args(const GemmArgs& a, int epi) {
   return kOk;
 }
 
-int pick_block_n(int N, int epi) {
+int pick_block_n(int N, int K, int epi) {
   if (epi == kEpiResidLN) return N;   // LayerNorm needs the whole row in one tile
   if (N <= 128) return N;
-  // epilogue-bound: four 128-column accumulator stages beat two 256-column ones unless the tail wastes too much
-  int best = 128, best_cost = 1 << 30;
-  for (int bn = 128; bn >= 64; bn -= 32) {
-    int cost = ceil_div(N, bn) * bn;
-    if (cost < best_cost) { best = bn; best_cost = cost; }
-  }
-  return best;
+  // long reductions are MMA/operand-bound: full-width 256-column MMAs, A streamed once
+  if (K >= 512 && N % 256 == 0 && (epi == kEpiBiasBf16 || epi == kEpiBiasF32)) return 256;
+  // epilogue-bound kernels: four 128-column accumulator stages (four epilogue warp groups).  Tiles start at
+  // multiples of 128 so the 128-byte output boxes never straddle two tiles; the N tail is clipped by TMA.
+  return 128;
 }
 
 int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   HS_TRY(gemm_check_args(a, epi));
-  const int block_n = pick_block_n(a.N, epi);
+  const int block_n = pick_block_n(a.N, a.K, epi);
   const int n_blks = ceil_div(a.N, block_n);
   const int m_blks = ceil_div(a.M, kBlockM);
   const int num_tiles = n_blks * m_blks;
-  const int stage_bytes = kATileBytes + block_n * 128;
-  int stages = kSmemBudget / stage_bytes;
-  if (stages > 8) stages = 8;
-  const int num_kb = ceil_div(a.K, kBlockK);
-  if (stages > num_kb * 2) stages = num_kb * 2 < 2 ? 2 : num_kb * 2;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-  CUtensorMap tmA, tmB;
-  HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tmA));
-  HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)block_n, &tmB));
+  CUtensorMap tm[4];
+  HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tm[0]));
+  HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)block_n, &tm[1]));
+  // output boxes: [32 rows x 128 bytes]
+  const uint64_t M = (uint64_t)a.M, N = (uint64_t)a.N;
   switch (epi) {
-    case kEpiBiasBf16: return launch_gemm<kEpiBiasBf16>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
-    case kEpiBiasF32:  return launch_gemm<kEpiBiasF32>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
-    case kEpiResidLN:  return launch_gemm<kEpiResidLN>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
-    case kEpiSwiGLU:   return launch_gemm<kEpiSwiGLU>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
-    case kEpiDSwiGLU:  return launch_gemm<kEpiDSwiGLU>(a, tmA, tmB, block_n, stages, n_blks, num_tiles, smem, stream);
+    case kEpiBiasBf16:
+      HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
+      tm[3] = tm[2];
+      return launch_gemm<kEpiBiasBf16>(a, tm, block_n, n_blks, num_tiles, stream);
+    case kEpiBiasF32:
+      HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 32, 32, &tm[2], 4));
+      tm[3] = tm[2];
+      return launch_gemm<kEpiBiasF32>(a, tm, block_n, n_blks, num_tiles, stream);
+    case kEpiResidLN:
+      HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 32, 32, &tm[2], 4));
+      if (a.gamma) HS_TRY(get_tmap(a.out1, N, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
+      else tm[3] = tm[2];
+      return launch_gemm<kEpiResidLN>(a, tm, block_n, n_blks, num_tiles, stream);
+    case kEpiSwiGLU:
+      HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
+      HS_TRY(get_tmap(a.out1, N / 2, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
+      return launch_gemm<kEpiSwiGLU>(a, tm, block_n, n_blks, num_tiles, stream);
+    case kEpiDSwiGLU:
+      HS_TRY(get_tmap(a.out0, 2 * N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
+      tm[3] = tm[2];
+      return launch_gemm<kEpiDSwiGLU>(a, tm, block_n, n_blks, num_tiles, stream);
   }
   set_error("gemm: bad epilogue %d", epi);
   return kInvalidArgument;
@@ -662,7 +898,8 @@ int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
   const int tiles_r = ceil_div(a.Nout, kBlockM);
   const int num_tiles = tiles_r * tiles_c;
   const int kb_total = ceil_div(a.Mred, 64);
-  int splits = ceil_div(kNumSMs, num_tiles);
+  int splits = kNumSMs / num_tiles;   // one wave: never more CTAs than SMs
+  if (splits < 1) splits = 1;
   if (splits > kb_total) splits = kb_total;
   const int kb_per = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, kb_per);

@@ -1,4 +1,5 @@
 // LayerNorm backward and short-sequence attention (forward + backward).
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace hsimae {
@@ -473,9 +474,20 @@ static int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream) {
   return kOk;
 }
 
+bool attn_mma_supported(const AttnArgs& a);
+int launch_attn_mma_fwd(const AttnArgs& a, cudaStream_t stream);
+int launch_attn_mma_bwd(const AttnArgs& a, cudaStream_t stream);
+
+// HSIMAE_ATTN_SIMT=1 forces the CUDA-core kernels (kept for groups longer than 40 tokens and as an A/B checker)
+static bool attn_use_mma(const AttnArgs& a) {
+  static const bool force_simt = getenv("HSIMAE_ATTN_SIMT") && atoi(getenv("HSIMAE_ATTN_SIMT")) != 0;
+  return !force_simt && attn_mma_supported(a);
+}
+
 int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream) {
   HS_TRY(attn_check(a));
   if (a.N == 0) return kOk;
+  if (attn_use_mma(a)) return launch_attn_mma_fwd(a, stream);
   switch (a.D / a.heads) {
     case 8: return attn_fwd_launch<8>(a, stream);
     case 16: return attn_fwd_launch<16>(a, stream);
@@ -487,6 +499,7 @@ int launch_attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   HS_TRY(attn_check(a));
   HS_REQUIRE(a.lse && a.dout && a.dqkv, "attention bwd: missing buffers");
   if (a.N == 0) return kOk;
+  if (attn_use_mma(a)) return launch_attn_mma_bwd(a, stream);
   switch (a.D / a.heads) {
     case 8: return attn_bwd_launch<8>(a, stream);
     case 16: return attn_bwd_launch<16>(a, stream);
