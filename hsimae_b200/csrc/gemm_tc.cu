@@ -171,7 +171,10 @@ struct TmemAcc {
 // the row-wise reference epilogues in epilogue.cuh (the checker path).
 // ---------------------------------------------------------------------------
 constexpr int kStageBufBytes = 32 * 128;   // one box
-constexpr int kStageBufsPerWarp = 2;
+// staging boxes per epilogue warp: the gate epilogue fills two boxes at once (a|b and gate); the others reuse a
+// single box (the TMA unit has read it long before the next one is assembled), which leaves the shared memory
+// to the operand pipeline -- these GEMMs are bound by bytes in flight from L2/HBM, not by the epilogue.
+template <int EPI> struct StagingBufs { static constexpr int value = EPI == kEpiSwiGLU ? 2 : 1; };
 
 struct Stager {
   uint32_t base;     // smem address of this warp's two 4 KB buffers (1024-byte aligned)
@@ -186,15 +189,9 @@ struct Stager {
       pending = false;
     }
   }
-  // strict alternation: the most recent store read the OTHER buffer and may stay in flight
-  __device__ __forceinline__ int begin_box() {
-    if (pending) {
-      if (lane == 0) ptx::bulk_wait_read1();
-      __syncwarp();
-    }
-    return cur;
-  }
-  __device__ __forceinline__ void end_box(const CUtensorMap* tm, int col, int row) { flush(cur, tm, col, row); cur ^= 1; }
+  // single-buffer use: wait until the previous store has been read, then refill buffer 0
+  __device__ __forceinline__ int begin_box() { acquire(); return 0; }
+  __device__ __forceinline__ void end_box(const CUtensorMap* tm, int col, int row) { flush(0, tm, col, row); }
   // 16-byte piece j (0..7) of this lane's 128-byte box row; 128B-swizzle: piece index XOR (row & 7)
   __device__ __forceinline__ void put(int b, int j, uint4 v) {
     ptx::st_shared_v4(base + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v);
@@ -230,7 +227,7 @@ __device__ __forceinline__ void tc_bias_chunk(const GemmArgs& p, TmemAcc& acc, S
     for (int i = 0; i < W / 4; ++i) st.put(b, i, pack4_f32(v + 4 * i));
     st.end_box(tmO, n0 + c, m0);
   } else {
-    const int b = (c & 63) == 0 ? st.begin_box() : st.cur;
+    const int b = (c & 63) == 0 ? st.begin_box() : 0;
     const int j0 = (c & 63) >> 3;
 #pragma unroll
     for (int i = 0; i < W / 8; ++i) st.put(b, j0 + i, pack8_bf16(v + 8 * i));
@@ -287,7 +284,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
         o[i] = dg[i] * b * (sg * (1.0f + a * (1.0f - sg)));
         o[16 + i] = dg[i] * (a * sg);
       }
-      const int b = (c & 31) == 0 ? st.begin_box() : st.cur;
+      const int b = (c & 31) == 0 ? st.begin_box() : 0;
       const int j0 = ((c & 31) >> 4) * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) st.put(b, j0 + i, pack8_bf16(o + 8 * i));
@@ -346,7 +343,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
           v[i + 2] = fmaf((v[i + 2] - mean) * rstd, g.z, be.z);
           v[i + 3] = fmaf((v[i + 3] - mean) * rstd, g.w, be.w);
         }
-        const int b = (c & 63) == 0 ? st.begin_box() : st.cur;
+        const int b = (c & 63) == 0 ? st.begin_box() : 0;
         const int j0 = (c & 63) >> 3;
 #pragma unroll
         for (int i = 0; i < W / 8; ++i) st.put(b, j0 + i, pack8_bf16(v + 8 * i));
@@ -414,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   constexpr uint32_t kAccStride = 512 / S;
-  constexpr uint32_t kStagingBytes = 4 * S * kStageBufsPerWarp * kStageBufBytes;
+  constexpr uint32_t kStagingBytes = 4 * S * StagingBufs<EPI>::value * kStageBufBytes;
 
   const uint32_t b_bytes = (uint32_t)block_n * 128u;
   const uint32_t stage_bytes = kATileBytes + b_bytes;
@@ -493,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;   // accumulator stage served by this warp's group
-    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (kStageBufsPerWarp * kStageBufBytes), lane, false, 0};
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI>::value * kStageBufBytes), lane, false, 0};
     int it = grp;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += S * gridDim.x, it += S) {
       const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
@@ -773,7 +770,7 @@ int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_b
     configured = true;
   }
   // shared memory: [operand pipeline stages][epilogue staging boxes][barriers]; as many stages as fit
-  const int staging = 4 * S * kStageBufsPerWarp * kStageBufBytes;
+  const int staging = 4 * S * StagingBufs<EPI>::value * kStageBufBytes;
   const int stage_bytes = kATileBytes + block_n * 128;
   const int num_kb = ceil_div(a.K, kBlockK);
   int stages = (kSmemMax - staging - 2048) / stage_bytes;

@@ -162,75 +162,90 @@ embed_fwd_kernel(EmbedArgs a) {
 
 // Specialisation for a compile-time patch geometry (the reference's 8x3x3 patches of a 9x9 cube): the (u,p,q)
 // loops unroll into immediate shared-memory offsets, so the inner loop is one broadcast LDS + one FFMA per MAC.
+// Two samples are in flight per CTA (one per 256-thread half) sharing the transposed weight tile in smem: twice
+// the warps per SM to cover the broadcast-LDS -> FFMA latency.
+constexpr int kEmbedSlots = 2;
+
 template <int U, int P, int IMG, int TK>
-__global__ void __launch_bounds__(kEmbedThreads)
+__global__ void __launch_bounds__(kEmbedThreads * kEmbedSlots)
 embed_fwd_fixed_kernel(EmbedArgs a) {
   extern __shared__ float sm[];
   const PatchGeom g = a.g;
   constexpr int PK = U * P * P;
   const int D = a.D, K = a.K;
-  float* sW = sm;                         // [PK][D]
-  float* sCube = sW + (size_t)PK * D;     // [cube]
-  float* sX = sCube + g.cube;             // [K][D]
-  int* sBase = reinterpret_cast<int*>(sX + (size_t)K * D);  // [K] cube offset of each kept token
-  int* sTok = sBase + K;                  // [K]
+  const int slot = threadIdx.x / kEmbedThreads, tid = threadIdx.x % kEmbedThreads;
+  float* sW = sm;                                              // [PK][D] shared by both slots
+  const size_t slot_floats = ((size_t)g.cube + (size_t)K * D + 2 * (size_t)K + 3) / 4 * 4;   // keep every slot 16-byte aligned
+  float* sCube = sW + (size_t)PK * D + slot * slot_floats;     // [cube]
+  float* sX = sCube + g.cube;                                  // [K][D]
+  int* sBase = reinterpret_cast<int*>(sX + (size_t)K * D);     // [K] cube offset of each kept token
+  int* sTok = sBase + K;                                       // [K]
   for (int i = threadIdx.x; i < PK * D; i += blockDim.x) {
     const int d = i / PK, j = i - d * PK;
     sW[(size_t)j * D + d] = a.W[i];
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+  const int warp = tid >> 5, lane = tid & 31, nwarps = kEmbedThreads >> 5;
+  const int rounds = (a.N + gridDim.x * kEmbedSlots - 1) / (gridDim.x * kEmbedSlots);
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int n = (rd * gridDim.x + blockIdx.x) * kEmbedSlots + slot;
+    const bool live = n < a.N;
     __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
-    for (int i = threadIdx.x; i < g.cube / 4; i += blockDim.x) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-      const int tok = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
-      sTok[i] = tok;
-      sBase[i] = cube_index(g, tok, 0);
-    }
-    __syncthreads();
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-      const float b = a.bias ? a.bias[d] : 0.f;
-      for (int k0 = 0; k0 < K; k0 += TK) {
-        float acc[TK];
-        const float* base[TK];
-#pragma unroll
-        for (int k = 0; k < TK; ++k) { acc[k] = 0.f; base[k] = sCube + sBase[k0 + k < K ? k0 + k : K - 1]; }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int pp = 0; pp < P; ++pp)
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-              const float w = sW[(size_t)((u * P + pp) * P + q) * D + d];
-#pragma unroll
-              for (int k = 0; k < TK; ++k) acc[k] = fmaf(base[k][(u * IMG + pp) * IMG + q], w, acc[k]);
-            }
-#pragma unroll
-        for (int k = 0; k < TK; ++k)
-          if (k0 + k < K) sX[(size_t)(k0 + k) * D + d] = acc[k] + b + __ldg(a.pos + (size_t)sTok[k0 + k] * D + d);
+    if (live) {
+      const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
+      for (int i = tid; i < g.cube / 4; i += kEmbedThreads) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+      for (int i = tid; i < K; i += kEmbedThreads) {
+        const int tok = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
+        sTok[i] = tok;
+        sBase[i] = cube_index(g, tok, 0);
       }
     }
     __syncthreads();
-    for (int k = warp; k < K; k += nwarps) {
-      const float* xr = sX + (size_t)k * D;
-      const size_t m = (size_t)n * K + k;
-      float s = 0.f;
-      for (int i = lane; i < D; i += 32) s += xr[i];
-      const float mean = warp_sum(s) / D;
-      float sq = 0.f;
-      for (int i = lane; i < D; i += 32) { const float dv = xr[i] - mean; sq = fmaf(dv, dv, sq); }
-      const float rstd = rsqrtf(warp_sum(sq) / D + a.eps);
-      for (int i = lane; i < D; i += 32) {
-        const float v = xr[i];
-        a.x[m * D + i] = v;
-        const float xh = (v - mean) * rstd;
-        if (a.ln_a) a.ln_a[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_a[i], a.beta_a[i]));
-        if (a.ln_b) a.ln_b[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_b[i], a.beta_b[i]));
+    if (live) {
+      for (int d = tid; d < D; d += kEmbedThreads) {
+        const float b = a.bias ? a.bias[d] : 0.f;
+        for (int k0 = 0; k0 < K; k0 += TK) {
+          float acc[TK];
+          const float* base[TK];
+#pragma unroll
+          for (int k = 0; k < TK; ++k) { acc[k] = 0.f; base[k] = sCube + sBase[k0 + k < K ? k0 + k : K - 1]; }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp)
+#pragma unroll
+              for (int q = 0; q < P; ++q) {
+                const float w = sW[(size_t)((u * P + pp) * P + q) * D + d];
+#pragma unroll
+                for (int k = 0; k < TK; ++k) acc[k] = fmaf(base[k][(u * IMG + pp) * IMG + q], w, acc[k]);
+              }
+#pragma unroll
+          for (int k = 0; k < TK; ++k)
+            if (k0 + k < K) sX[(size_t)(k0 + k) * D + d] = acc[k] + b + __ldg(a.pos + (size_t)sTok[k0 + k] * D + d);
+        }
       }
-      if (lane == 0) {
-        if (a.stats_a) { a.stats_a[2 * m] = mean; a.stats_a[2 * m + 1] = rstd; }
-        if (a.stats_b) { a.stats_b[2 * m] = mean; a.stats_b[2 * m + 1] = rstd; }
+    }
+    __syncthreads();
+    if (live) {
+      for (int k = warp; k < K; k += nwarps) {
+        const float* xr = sX + (size_t)k * D;
+        const size_t m = (size_t)n * K + k;
+        float s = 0.f;
+        for (int i = lane; i < D; i += 32) s += xr[i];
+        const float mean = warp_sum(s) / D;
+        float sq = 0.f;
+        for (int i = lane; i < D; i += 32) { const float dv = xr[i] - mean; sq = fmaf(dv, dv, sq); }
+        const float rstd = rsqrtf(warp_sum(sq) / D + a.eps);
+        for (int i = lane; i < D; i += 32) {
+          const float v = xr[i];
+          a.x[m * D + i] = v;
+          const float xh = (v - mean) * rstd;
+          if (a.ln_a) a.ln_a[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_a[i], a.beta_a[i]));
+          if (a.ln_b) a.ln_b[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_b[i], a.beta_b[i]));
+        }
+        if (lane == 0) {
+          if (a.stats_a) { a.stats_a[2 * m] = mean; a.stats_a[2 * m + 1] = rstd; }
+          if (a.stats_b) { a.stats_b[2 * m] = mean; a.stats_b[2 * m + 1] = rstd; }
+        }
       }
     }
   }
@@ -247,9 +262,11 @@ int launch_embed_fwd(const EmbedArgs& a, cudaStream_t stream) {
   const size_t smem = embed_fwd_smem(a);
   HS_REQUIRE(smem <= 227 * 1024, "embed: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
   const int grid = a.N < kNumSMs ? a.N : kNumSMs;
-  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9) {
-    HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_fixed_kernel<8, 3, 9, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    embed_fwd_fixed_kernel<8, 3, 9, 9><<<grid, kEmbedThreads, smem, stream>>>(a);
+  const size_t smem2 = ((size_t)a.g.PK * a.D + kEmbedSlots * (((size_t)a.g.cube + (size_t)a.K * a.D + 2 * (size_t)a.K + 3) / 4 * 4)) * sizeof(float);
+  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9 && smem2 <= 227 * 1024) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_fixed_kernel<8, 3, 9, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const int grid2 = ceil_div(a.N, kEmbedSlots) < kNumSMs ? ceil_div(a.N, kEmbedSlots) : kNumSMs;
+    embed_fwd_fixed_kernel<8, 3, 9, 9><<<grid2, kEmbedThreads * kEmbedSlots, smem2, stream>>>(a);
   } else {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     embed_fwd_kernel<<<grid, kEmbedThreads, smem, stream>>>(a);
@@ -364,7 +381,7 @@ int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream) {
   if (a.N == 0) return kOk;
   const size_t smem = (size_t)a.g.cube * sizeof(float) + ((size_t)a.K * a.g.PK + a.K) * sizeof(int);
   HS_REQUIRE(smem <= 227 * 1024, "embed_bwd: needs %zu bytes of shared memory", smem);
-  const int grid = a.N < kNumSMs ? a.N : kNumSMs;
+  const int grid = a.N < 2 * kNumSMs ? a.N : 2 * kNumSMs;   // two CTAs per SM
   if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_fixed_kernel<8, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     embed_bwd_fixed_kernel<8, 3, 9><<<grid, 256, smem, stream>>>(a);
