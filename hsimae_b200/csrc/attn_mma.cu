@@ -100,7 +100,7 @@ struct Geo {
   uint32_t a_off, a_off_o;        // A operand (16 tile rows)
   uint32_t b_off[NP], b_off_o[NP];    // B = X^T operand: column-tile pairs
   uint32_t bc_off[NP], bc_off_o[NP];  // B = X operand (transposed load): k-steps of 16 column tokens
-  uint32_t mask;                  // bit (4*nt + e): accumulator element e of column tile nt is a valid (row, col) pair
+  float madd[NT][4];              // additive mask: 0 where accumulator element (nt, e) is a valid (row, col) pair, -inf elsewhere
   int r_tok[2]; bool r_ok[2];     // accumulator rows g, g+8
   int c_tok[NT][2];               // accumulator columns nt*8 + 2t + {0,1}
 };
@@ -122,12 +122,11 @@ __device__ __forceinline__ Geo<NT> make_geo(const Unit& t, int lane, int pitch, 
     q.b_off[i] = (uint32_t)(bt * pitch + b_co * 2);   q.b_off_o[i] = (uint32_t)(bt * pitch_o + b_co * 2);
     q.bc_off[i] = (uint32_t)(ct * pitch + bc_co * 2); q.bc_off_o[i] = (uint32_t)(ct * pitch_o + bc_co * 2);
   }
-  q.mask = 0;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      if (t.pair_valid(g + (e >> 1) * 8, nt * 8 + 2 * tq + (e & 1))) q.mask |= 1u << (4 * nt + e);
+      q.madd[nt][e] = t.pair_valid(g + (e >> 1) * 8, nt * 8 + 2 * tq + (e & 1)) ? 0.f : -INFINITY;
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) { q.r_ok[hf] = t.row_valid(g + hf * 8); q.r_tok[hf] = t.row_token(g + hf * 8); }
 #pragma unroll
@@ -260,7 +259,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) sc[nt][e] = (q.mask >> (4 * nt + e)) & 1u ? sc[nt][e] * scale_log2 : -INFINITY;
+          for (int e = 0; e < 4; ++e) sc[nt][e] = fmaf(sc[nt][e], scale_log2, q.madd[nt][e]);
           mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
           mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
         }
@@ -388,7 +387,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float lse = (e >> 1) ? lse1 : lse0, de = (e >> 1) ? de1 : de0;
-              const float p = (q.mask >> (4 * nt + e)) & 1u ? fast_exp2(sc[nt][e] * scale_log2 - lse) : 0.f;
+              const float p = fast_exp2(fmaf(sc[nt][e], scale_log2, q.madd[nt][e]) - lse);
               sc[nt][e] = p * (dp[nt][e] - de) * scale;     // dS
             }
           }
@@ -406,7 +405,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int tc = q.c_tok[nt][e & 1];
-              const float p = (q.mask >> (4 * nt + e)) & 1u ? fast_exp2(sc[nt][e] * scale_log2 - ls[tc * H + h]) : 0.f;
+              const float p = fast_exp2(fmaf(sc[nt][e], scale_log2, q.madd[nt][e]) - ls[tc * H + h]);
               dp[nt][e] = p * (dp[nt][e] - dl[tc * H + h]) * scale;   // dS^T
               sc[nt][e] = p;                                           // P^T
             }

@@ -235,18 +235,22 @@ __device__ __forceinline__ void tc_bias_chunk(const GemmArgs& p, TmemAcc& acc, S
   }
 }
 
-template <int EPI>
+// `wait_acc()` blocks until the tile's accumulator is complete; epilogues that read per-row global inputs issue
+// the first loads BEFORE calling it, so that latency overlaps the tail of the MMA.
+template <int EPI, bool PREFETCH, class Wait>
 __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Stager& st, const CUtensorMap* tmO0,
-                                            const CUtensorMap* tmO1, int m0, int lane, int n0, int width) {
+                                            const CUtensorMap* tmO1, int m0, int lane, int n0, int width, Wait wait_acc) {
   const int m = m0 + lane;
   const bool valid = m < p.M;
   if constexpr (EPI == kEpiBiasBf16 || EPI == kEpiBiasF32) {
     constexpr bool F32 = EPI == kEpiBiasF32;
+    wait_acc();
     int c = 0;
     for (; c + 32 <= width; c += 32) tc_bias_chunk<32, F32>(p, acc, st, tmO0, m0, n0, c, width);
     for (; c + 16 <= width; c += 16) tc_bias_chunk<16, F32>(p, acc, st, tmO0, m0, n0, c, width);
   } else if constexpr (EPI == kEpiSwiGLU) {
     // tile of packed (a|b interleaved by 16) columns; buffer 0: a|b boxes (64 packed columns), buffer 1: the gate box
+    wait_acc();
     for (int c = 0; c + 32 <= width; c += 32) {
       float v[32];
       acc.template load<32>(c, v);
@@ -267,15 +271,29 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
     }
     st.flush(1, tmO1, n0 >> 1, m0);
   } else if constexpr (EPI == kEpiDSwiGLU) {
-    // tile of hidden columns; every 16 of them become 32 packed output columns
+    // tile of hidden columns; every 16 of them become 32 packed output columns.  The saved pre-activations of the
+    // NEXT chunk are fetched while the current one is being processed (the first fetch overlaps the MMA tail).
+    const __nv_bfloat16* abrow = p.ab + (size_t)(valid ? m : 0) * p.ldab + 2 * n0;
+    uint4 nxt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nxt[i] = valid ? *reinterpret_cast<const uint4*>(abrow + 8 * i) : make_uint4(0u, 0u, 0u, 0u);  // L1-allocating: the 4 loads share one line
+    wait_acc();
     for (int c = 0; c + 16 <= width; c += 16) {
+      uint4 cur[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      if (c + 32 <= width && valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nxt[i] = *reinterpret_cast<const uint4*>(abrow + 2 * (c + 16) + 8 * i);
+      }
       float dg[16];
       acc.template load<16>(c, dg);
       float ab[32], o[32];
-      if (valid) load_bf16_row<32>(p.ab + (size_t)m * p.ldab + 2 * (n0 + c), ab);
-      else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) ab[i] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const float2 x0 = unpack_bf16x2(cur[i].x), x1 = unpack_bf16x2(cur[i].y), x2 = unpack_bf16x2(cur[i].z), x3 = unpack_bf16x2(cur[i].w);
+        ab[8 * i] = x0.x; ab[8 * i + 1] = x0.y; ab[8 * i + 2] = x1.x; ab[8 * i + 3] = x1.y;
+        ab[8 * i + 4] = x2.x; ab[8 * i + 5] = x2.y; ab[8 * i + 6] = x3.x; ab[8 * i + 7] = x3.y;
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -295,13 +313,24 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
     const bool ln = p.gamma != nullptr;
     const float s = valid ? row_scale(p.rs, m) : 1.0f;
     float sum = 0.f;
+    // residual chunk of 32 columns, fetched one chunk ahead (the first fetch overlaps the MMA tail)
+    const float* rrow = p.resid + (size_t)(valid ? m : 0) * p.ldr;
+    float rnext[32];   // only live when PREFETCH
+    if constexpr (PREFETCH) { if (width >= 32) load_f32_row<32>(rrow, rnext); }
+    wait_acc();
     auto pass1 = [&](auto wtag, int c) {
       constexpr int W = decltype(wtag)::value;
       float v[W];
       acc.template load<W>(c, v);
       if (valid) {
         float r[W];
-        load_f32_row<W>(p.resid + (size_t)m * p.ldr + c, r);
+        if constexpr (W == 32 && PREFETCH) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = rnext[i];
+          if (c + 64 <= width) load_f32_row<32>(rrow + c + 32, rnext);
+        } else {
+          load_f32_row<W>(rrow + c, r);
+        }
         if (p.bias) add_vec<W>(p.bias + c, v);
 #pragma unroll
         for (int i = 0; i < W; ++i) v[i] = fmaf(s, v[i], r[i]);
@@ -495,12 +524,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += S * gridDim.x, it += S) {
       const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
       const uint32_t aphase = (uint32_t)(it / S) & 1u;
-      ptx::mbar_wait(tfull + grp, aphase);
-      ptx::tc_fence_after();
       TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
       const int n0 = n_blk * block_n;
       int width = p.N - n0; if (width > block_n) width = block_n;
-      tc_epilogue<EPI>(p, acc, st, &tmO0, &tmO1, m_blk * kBlockM + q * 32, lane, n0, width);
+      tc_epilogue<EPI, (S == 2)>(p, acc, st, &tmO0, &tmO1, m_blk * kBlockM + q * 32, lane, n0, width,
+                       [&]() { ptx::mbar_wait(tfull + grp, aphase); ptx::tc_fence_after(); });
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty + grp);
     }
