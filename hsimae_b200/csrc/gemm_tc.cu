@@ -801,9 +801,14 @@ int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_b
   const int staging = 4 * S * StagingBufs<EPI>::value * kStageBufBytes;
   const int stage_bytes = kATileBytes + block_n * 128;
   const int num_kb = ceil_div(a.K, kBlockK);
-  int stages = (kSmemMax - staging - 2048) / stage_bytes;
+  // epilogues that read per-row global inputs (saved pre-activations, residual) rely on L1 to merge each thread's
+  // 16-byte loads of one line: leave ~36 KB of the 228 KB shared/L1 array to the cache for them
+  const int smem_cap = (EPI == kEpiDSwiGLU || EPI == kEpiResidLN) ? kSmemMax - 36 * 1024 : kSmemMax;
+  int stages = (smem_cap - staging - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > 2 * num_kb) stages = 2 * num_kb;
+  static const int stage_cap = getenv("HSIMAE_GEMM_STAGES") ? atoi(getenv("HSIMAE_GEMM_STAGES")) : 0;   // tuning experiments
+  if (stage_cap > 0 && stages > stage_cap) stages = stage_cap;
   if (stages < 2) stages = 2;
   const size_t smem = (size_t)stages * stage_bytes + staging + 1024 + 512;
   HS_REQUIRE(smem <= (size_t)kSmemMax, "gemm: tile N=%d needs %zu bytes of shared memory", block_n, smem);
