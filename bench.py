@@ -143,6 +143,24 @@ def time_events(fn, iters: int):
     return a.elapsed_time(b) * 1e-3 / iters
 
 
+def ncu_traffic(cand: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the candidate kernel, from the committed
+    `ncu --set full` capture (profiles/r01b_ncu_full_kernels.json; same shapes as timed here), or None"""
+    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_kernels.json")
+    want = {"gemm_tc_kernel<SwiGLU>": ("gemm_tc_kernel<3", 0), "gemm_tc_kernel<ResidLN>": ("gemm_tc_kernel<2", 0),
+            "gemm_tc_kernel<Bias> qkv": ("gemm_tc_kernel<0, 4", 0), "wgrad_tc_kernel dW13": ("wgrad_tc_kernel", 0),
+            "gemm_tc_kernel<Bias> dgrad": ("gemm_tc_kernel<0, 2", 0)}
+    try:
+        rows = json.load(open(path))
+        for key, (prefix, nth) in want.items():
+            if cand.startswith(key):
+                hits = [r for r in rows if prefix in r["kernel"]]
+                return (hits[nth]["dram_read_mb"] + hits[nth]["dram_write_mb"]) * 1e6
+    except Exception:
+        pass
+    return None
+
+
 def dominant_kernel_roofline(batch: int, pk):
     """Times the per-block GEMM kernels at the bench shapes (M = batch*18 encoder token rows) in isolation, picks the
     class with the largest share of a step, and reports it against its binding roofline."""
@@ -181,7 +199,7 @@ def dominant_kernel_roofline(batch: int, pk):
     else:
         ach = r["flops"] / r["t"] / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"]}
-    roof.update(kernel=name, us_per_launch=r["t"] * 1e6, traffic=None, peak_source=pk["src"],
+    roof.update(kernel=name, us_per_launch=r["t"] * 1e6, traffic=ncu_traffic(name), peak_source=pk["src"],
                 algorithmic_bytes=r["bytes"], algorithmic_flops=r["flops"],
                 all_kernels={k: {"us": v["t"] * 1e6, "tflops": v["flops"] / v["t"] / 1e12, "gbs": v["bytes"] / v["t"] / 1e9}
                              for k, v in rows.items()})
