@@ -67,6 +67,8 @@ PROTOTYPES = {
     "hsimae_encoder_workspace_bytes": (c_i64, [c_void_p, c_i32, c_i32, c_i32, c_i32]),
     "hsimae_encoder_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p,
                                        C.POINTER(c_void_p), c_i32, c_void_p, c_i64, c_void_p]),
+    "hsimae_encoder_forward_scene": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_void_p, c_i64,
+                                             c_void_p]),
     "hsimae_encoder_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p,
                                         C.POINTER(c_void_p), c_void_p, c_i64, c_void_p, c_i32, c_void_p]),
     "hsimae_encoder_latent": (c_int, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p]),

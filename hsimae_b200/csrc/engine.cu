@@ -546,10 +546,11 @@ int64_t hsimae_encoder_workspace_bytes(const hsimae_plan* p, int32_t n, int32_t 
   return enc_layout(p, n, lt, ll, save != 0, nullptr).bytes;
 }
 
-int hsimae_encoder_forward(hsimae_plan* p, const void* wb, const void* wf, const float* imgs, int32_t n, int32_t lt, int32_t ll,
-                           const int32_t* ids, const float* const* drop, int32_t save, void* ws, int64_t ws_bytes, void* stream) {
+static int encoder_forward_impl(hsimae_plan* p, const void* wb, const void* wf, const float* imgs, const float* scene, int scene_w,
+                                long long pixel0, int32_t n, int32_t lt, int32_t ll, const int32_t* ids, const float* const* drop,
+                                int32_t save, void* ws, int64_t ws_bytes, void* stream) {
   HS_TRY(check_enc_args(p, n, lt, ll, ids));
-  HS_REQUIRE(wb && wf && imgs && ws, "encoder_forward: null argument");
+  HS_REQUIRE(wb && wf && (imgs || scene) && ws, "encoder_forward: null argument");
   EncLayout L = enc_layout(p, n, lt, ll, save != 0, ws);
   HS_REQUIRE(ws_bytes >= L.bytes, "encoder workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.bytes);
   if (n == 0) return kOk;
@@ -561,7 +562,7 @@ int hsimae_encoder_forward(hsimae_plan* p, const void* wb, const void* wf, const
   const bool fusion = !L.fu.empty();
 
   EmbedArgs e{};
-  e.g = p->g; e.N = n; e.K = L.K; e.D = D; e.imgs = imgs; e.W = wff + p->f_pe_w; e.bias = wff + p->f_pe_b; e.pos = wff + p->f_pos;
+  e.g = p->g; e.N = n; e.K = L.K; e.D = D; e.imgs = imgs; e.scene = scene; e.scene_w = scene_w; e.pixel0 = pixel0; e.W = wff + p->f_pe_w; e.bias = wff + p->f_pe_b; e.pos = wff + p->f_pos;
   e.ids_keep = ids; e.x = L.x0; e.eps = 1e-5f;
   if (split) {
     e.gamma_a = wff + p->b1[0].g1; e.beta_a = wff + p->b1[0].be1; e.ln_a = L.sp[0].ln1; e.stats_a = L.sp[0].stats1;
@@ -601,6 +602,23 @@ int hsimae_encoder_forward(hsimae_plan* p, const void* wb, const void* wf, const
     }
   }
   return kOk;
+}
+
+int hsimae_encoder_forward(hsimae_plan* p, const void* wb, const void* wf, const float* imgs, int32_t n, int32_t lt, int32_t ll,
+                           const int32_t* ids, const float* const* drop, int32_t save, void* ws, int64_t ws_bytes, void* stream) {
+  HS_REQUIRE(imgs != nullptr, "encoder_forward: null argument");
+  return encoder_forward_impl(p, wb, wf, imgs, nullptr, 0, 0, n, lt, ll, ids, drop, save, ws, ws_bytes, stream);
+}
+
+int hsimae_encoder_forward_scene(hsimae_plan* p, const void* wb, const void* wf, const float* scene, int32_t scene_h, int32_t scene_w,
+                                 int64_t pixel0, int32_t n, void* ws, int64_t ws_bytes, void* stream) {
+  HS_REQUIRE(p && scene, "encoder_forward_scene: null argument");
+  const int img = p->g.img;
+  HS_REQUIRE(scene_h >= img && scene_w >= img, "scene %dx%d smaller than the %dx%d window", scene_h, scene_w, img, img);
+  const int64_t windows = (int64_t)(scene_h - img + 1) * (scene_w - img + 1);
+  HS_REQUIRE(pixel0 >= 0 && n >= 0 && pixel0 + n <= windows, "window range [%lld, %lld) outside the %lld windows of the scene",
+             (long long)pixel0, (long long)(pixel0 + n), (long long)windows);
+  return encoder_forward_impl(p, wb, wf, nullptr, scene, scene_w, pixel0, n, p->g.T, p->g.L, nullptr, nullptr, 0, ws, ws_bytes, stream);
 }
 
 int hsimae_encoder_backward(hsimae_plan* p, const void* wb, const void* wf, const float* imgs, int32_t n, int32_t lt, int32_t ll,

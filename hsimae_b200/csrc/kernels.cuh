@@ -22,7 +22,11 @@ int launch_mask(const float* noise_t, const float* noise_l, int N, int T, int L,
 struct EmbedArgs {
   PatchGeom g;
   int N, K, D;                 // samples, kept tokens per sample, embed dim
-  const float* imgs;           // [N, cube]
+  const float* imgs;           // [N, cube]   (nullptr when `scene` is given)
+  // optional on-device sliding window: sample n is the img x img window whose top-left corner is pixel
+  // (pixel0 + n) of a [scene_h, scene_w, bands] HWC scene, row-major over (scene_h - img + 1) x (scene_w - img + 1)
+  // window positions (replaces the host-side cube materialisation of Utils/Preprocessing.py:205-213)
+  const float* scene; int scene_w; long long pixel0;
   const float* W;              // [D, PK]  (Conv3d weight viewed 2-D)
   const float* bias;           // [D]
   const float* pos;            // [P, D]

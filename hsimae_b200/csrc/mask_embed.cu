@@ -89,6 +89,28 @@ __device__ __forceinline__ int cube_index(const PatchGeom& g, int p, int j) {
   return ((t * g.u + u) * g.img + (h * g.p + pp)) * g.img + (w * g.p + q);
 }
 
+
+// cooperative load of sample n's cube into smem ([band][y][x], the layout of the reference's [N,1,bands,H,W] input):
+// either a contiguous cube, or gathered on the fly from an HWC scene (each pixel = `bands` contiguous floats)
+__device__ __forceinline__ void stage_cube(const EmbedArgs& a, const PatchGeom& g, int n, float* sCube, int tid, int nthreads) {
+  if (a.scene == nullptr) {
+    const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
+    for (int i = tid; i < g.cube / 4; i += nthreads) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+  } else {
+    const int wout = a.scene_w - g.img + 1;
+    const long long pix = a.pixel0 + n;
+    const int r = (int)(pix / wout), c = (int)(pix - (long long)r * wout);
+    const int quads = g.bands / 4, plane = g.img * g.img;
+    for (int i = tid; i < plane * quads; i += nthreads) {
+      const int px = i / quads, qd = i - px * quads;
+      const int y = px / g.img, x = px - y * g.img;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.scene + ((size_t)(r + y) * a.scene_w + (c + x)) * g.bands) + qd);
+      float* d = sCube + (size_t)(qd * 4) * plane + px;
+      d[0] = v.x; d[plane] = v.y; d[2 * plane] = v.z; d[3 * plane] = v.w;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kEmbedThreads)
 embed_fwd_kernel(EmbedArgs a) {
   extern __shared__ float sm[];
@@ -108,8 +130,7 @@ embed_fwd_kernel(EmbedArgs a) {
 
   for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
-    for (int i = threadIdx.x; i < g.cube / 4; i += blockDim.x) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+    stage_cube(a, g, n, sCube, threadIdx.x, blockDim.x);
     for (int i = threadIdx.x; i < K; i += blockDim.x) sTok[i] = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
     __syncthreads();
     for (int i = threadIdx.x; i < K * PK; i += blockDim.x) {
@@ -191,8 +212,7 @@ embed_fwd_fixed_kernel(EmbedArgs a) {
     const bool live = n < a.N;
     __syncthreads();
     if (live) {
-      const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
-      for (int i = tid; i < g.cube / 4; i += kEmbedThreads) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
+      stage_cube(a, g, n, sCube, tid, kEmbedThreads);
       for (int i = tid; i < K; i += kEmbedThreads) {
         const int tok = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
         sTok[i] = tok;
@@ -258,6 +278,8 @@ static size_t embed_fwd_smem(const EmbedArgs& a) {
 int launch_embed_fwd(const EmbedArgs& a, cudaStream_t stream) {
   HS_REQUIRE(a.g.cube % 4 == 0, "embed: cube size %d must be a multiple of 4", a.g.cube);
   HS_REQUIRE(a.K >= 1 && a.K <= a.g.P, "embed: bad K=%d", a.K);
+  HS_REQUIRE((a.imgs != nullptr) != (a.scene != nullptr), "embed: exactly one of imgs / scene must be given");
+  if (a.scene) HS_REQUIRE(a.g.bands % 4 == 0 && a.scene_w >= a.g.img, "embed: scene needs bands %% 4 == 0 and width >= window");
   if (a.N == 0) return kOk;
   const size_t smem = embed_fwd_smem(a);
   HS_REQUIRE(smem <= 227 * 1024, "embed: configuration needs %zu bytes of shared memory (> 227 KB)", smem);

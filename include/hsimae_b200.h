@@ -91,6 +91,13 @@ int64_t hsimae_encoder_workspace_bytes(const hsimae_plan* plan, int32_t n, int32
 int hsimae_encoder_forward(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, const float* imgs, int32_t n,
                            int32_t len_t, int32_t len_l, const int32_t* ids_keep32, const float* const* drop, int32_t save,
                            void* ws, int64_t ws_bytes, void* stream);
+/* Unmasked inference pass over sliding windows of an HWC scene that is resident in HBM: sample i is the
+ * img x img window whose top-left corner is window (pixel0 + i), windows enumerated row-major over
+ * (scene_h - img + 1) x (scene_w - img + 1).  Replaces the host-side per-pixel cube materialisation of
+ * Utils/Preprocessing.py:205-213 + the batch loop of Model_Finetuning.py:264-278 (workspace: save = 0 layout). */
+int hsimae_encoder_forward_scene(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, const float* scene,
+                                 int32_t scene_h, int32_t scene_w, int64_t pixel0, int32_t n, void* ws, int64_t ws_bytes,
+                                 void* stream);
 /* consumes the latent gradient left in the workspace by decoder/head backward.
  * `stages` is a bit mask (1: final norm + fusion blocks, 2: spectral encoder,
  * 4: spatial encoder + patch embedding); stages must be run in that order, 7 = all. */

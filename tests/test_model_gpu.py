@@ -286,3 +286,54 @@ def test_training_loop_decreases_loss():
         opt.zero_grad(); loss.backward(); opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5]) - 0.005, losses
+
+
+def test_scene_classification_matches_cube_batches_and_oracle():
+    """dense per-pixel inference (BASELINE config 5): on-device sliding windows == host-materialised cubes"""
+    import Models as M
+    from hsimae_b200.scene import classify_scene, symmetric_pad_hwc
+    g = tiny_geometry(17)
+    sd = O.make_state(g, seed=21, decoder=False, head=True, randomize_affine=True)
+    kw = {k: v for k, v in dict(TINY, num_class=17).items() if not k.startswith("decoder") and k != "norm_pix_loss"}
+    vit = M.HSIViT(**kw)
+    vit.load_state_dict({**vit.state_dict(), **sd})
+    vit = vit.to(DEV).eval()
+    torch.manual_seed(2)
+    H, W = 13, 11
+    scene = torch.randn(H, W, 32)
+    logits = classify_scene(vit, scene.to(DEV), batch=50)          # several partial batches
+    assert logits.shape == (H * W, 17)
+    # the reference's host path: symmetric padding + one cube per pixel (Utils/Preprocessing.py:205-213), HWC -> [1,C,H,W]
+    padded = np.pad(scene.numpy(), ((4, 4), (4, 4), (0, 0)), "symmetric")
+    assert np.array_equal(symmetric_pad_hwc(scene, 4).numpy(), padded)
+    cubes = np.stack([padded[r:r + 9, c:c + 9, :] for r in range(H) for c in range(W)])
+    x = torch.from_numpy(cubes).permute(0, 3, 1, 2).unsqueeze(1).contiguous()
+    with torch.no_grad():
+        via_cubes = vit(x.to(DEV))
+    assert torch.equal(logits, via_cubes)                            # same kernels, same values: bit-identical
+    ref = O.vit_forward(sd, x, g)
+    assert rel_err(logits, ref) < TOL_ACT
+    assert (logits[:, 1:].argmax(1).cpu() == ref[:, 1:].argmax(1)).float().mean() > 0.97
+
+
+def test_other_patch_geometry():
+    """a geometry other than the reference's 9x9x32 / 3x3x8 exercises the generic (non-specialised) kernels"""
+    import Models as M
+    kw = dict(img_size=8, patch_size=2, in_chans=1, bands=12, b_patch_size=4, embed_dim=64, depth=3, num_heads=4, s_depth=2,
+              decoder_embed_dim=32, decoder_depth=1, decoder_num_heads=4, norm_pix_loss=True, trunc_init=True)
+    g = O.Geometry(img_size=8, patch_size=2, bands=12, b_patch_size=4, embed_dim=64, depth=3, s_depth=2, num_heads=4,
+                   decoder_embed_dim=32, decoder_depth=1, decoder_num_heads=4)
+    sd = O.make_state(g, seed=4, randomize_affine=True)
+    model = M.HSIMAE(**kw)
+    model.load_state_dict({**model.state_dict(), **sd})
+    model = model.to(DEV)
+    torch.manual_seed(8); random.seed(8)
+    x = torch.randn(9, 1, 12, 8, 8, device=DEV)
+    loss, pred, mask = model(x, mask_ratio=0.6)
+    loss.backward()
+    aux = model._last
+    out, grads = O.pretrain_step_grads(sd, x.cpu(), g, aux["noise_t"].cpu(), aux["noise_l"].cpu(), aux["lt"], aux["ll"])
+    assert torch.equal(aux["ids_keep"].cpu(), out["ids_keep"]) and torch.equal(mask.cpu(), out["mask_img"])
+    assert abs(loss.item() - out["loss"].item()) <= TOL_LOSS * abs(out["loss"].item())
+    assert rel_err(pred, out["pred_img"]) < TOL_ACT
+    _check_grads(model, grads)
