@@ -153,7 +153,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // accumulator row of this thread in TMEM (lane = row, column = n)
 struct TmemAcc {
   uint32_t base;  // (lane_base << 16) | column_base
+  bool skip = false;   // tuning experiments only
   template <int W> __device__ __forceinline__ void load(int c, float (&v)[W]) {
+    if (skip) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[i] = 1.0f;
+      return;
+    }
     if constexpr (W == 32) ptx::tmem_ld32(base + c, v); else ptx::tmem_ld16(base + c, v);
     ptx::tmem_ld_wait();
   }
@@ -180,7 +186,9 @@ struct Stager {
   uint32_t base;     // smem address of this warp's two 4 KB buffers (1024-byte aligned)
   int lane;
   bool pending;      // a committed store may still be reading the buffers
-  int cur = 0;       // buffer being filled when the two are used in strict alternation
+  int cur = 0;       // (unused)
+  bool mute = false; // tuning experiments: do not issue the stores
+  bool nofence = false;
   // wait until the TMA unit has finished reading every box this warp handed over
   __device__ __forceinline__ void acquire() {
     if (pending) {
@@ -197,9 +205,9 @@ struct Stager {
     ptx::st_shared_v4(base + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v);
   }
   __device__ __forceinline__ void flush(int b, const CUtensorMap* tm, int col, int row) {
-    ptx::fence_proxy_async();
+    if (!nofence) ptx::fence_proxy_async();
     __syncwarp();
-    if (lane == 0) { ptx::tma_store_2d(tm, base + (uint32_t)b * kStageBufBytes, col, row); ptx::bulk_commit(); }
+    if (lane == 0 && !mute) { ptx::tma_store_2d(tm, base + (uint32_t)b * kStageBufBytes, col, row); ptx::bulk_commit(); }
     pending = true;
   }
 };
@@ -237,11 +245,13 @@ __device__ __forceinline__ void tc_bias_chunk(const GemmArgs& p, TmemAcc& acc, S
 
 // `wait_acc()` blocks until the tile's accumulator is complete; epilogues that read per-row global inputs issue
 // the first loads BEFORE calling it, so that latency overlaps the tail of the MMA.
-template <int EPI, bool PREFETCH, class Wait>
+template <int EPI, int MODE, class Wait>
 __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Stager& st, const CUtensorMap* tmO0,
                                             const CUtensorMap* tmO1, int m0, int lane, int n0, int width, Wait wait_acc) {
   const int m = m0 + lane;
   const bool valid = m < p.M;
+  constexpr bool PREFETCH = (MODE & 1) != 0;   // fetch the residual one chunk ahead (needs the registers of the S=2 variant)
+  constexpr bool G_DIRECT = (MODE & 2) != 0;   // gate values go to global memory straight from registers (one staging box per warp)
   if constexpr (EPI == kEpiBiasBf16 || EPI == kEpiBiasF32) {
     constexpr bool F32 = EPI == kEpiBiasF32;
     wait_acc();
@@ -265,11 +275,16 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
       const int j0 = (c & 63) >> 3;
 #pragma unroll
       for (int i = 0; i < 4; ++i) st.put(0, j0 + i, pack8_bf16(v + 8 * i));
-      st.put(1, (c >> 5) * 2, pack8_bf16(g));
-      st.put(1, (c >> 5) * 2 + 1, pack8_bf16(g + 8));
+      if constexpr (G_DIRECT) {
+        // 32 contiguous bytes per thread = one full sector
+        if (valid) store_bf16_row<16>(reinterpret_cast<__nv_bfloat16*>(p.out1) + (size_t)m * p.ld1 + ((n0 + c) >> 1), g);
+      } else {
+        st.put(1, (c >> 5) * 2, pack8_bf16(g));
+        st.put(1, (c >> 5) * 2 + 1, pack8_bf16(g + 8));
+      }
       if (((c + 32) & 63) == 0 || c + 32 >= width) st.flush(0, tmO0, n0 + (c & ~63), m0);
     }
-    st.flush(1, tmO1, n0 >> 1, m0);
+    if constexpr (!G_DIRECT) st.flush(1, tmO1, n0 >> 1, m0);
   } else if constexpr (EPI == kEpiDSwiGLU) {
     // tile of hidden columns; every 16 of them become 32 packed output columns.  The saved pre-activations of the
     // NEXT chunk are fetched while the current one is being processed (the first fetch overlaps the MMA tail).
@@ -481,9 +496,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty + stage, phase ^ 1u);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          if (p.dbg & 8) { ptx::mbar_arrive(full + stage); }
+          else {
           ptx::mbar_expect_tx(full + stage, stage_bytes);
           ptx::tma_load_2d(sa, &tmA, full + stage, kb * kBlockK, m_blk * kBlockM);
           ptx::tma_load_2d(sa + kATileBytes, &tmB, full + stage, kb * kBlockK, n_blk * block_n);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -505,10 +523,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sa + kATileBytes, 16, 1024);
+          if (!(p.dbg & 4)) {
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 K-elements = 32 bytes inside the 128B swizzle row
             ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           }
           ptx::umma_commit(empty + stage);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -519,20 +539,141 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;   // accumulator stage served by this warp's group
-    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI>::value * kStageBufBytes), lane, false, 0};
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI>::value * kStageBufBytes), lane, false, 0, (p.dbg & 1) != 0, (p.dbg & 16) != 0};
     int it = grp;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += S * gridDim.x, it += S) {
       const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
       const uint32_t aphase = (uint32_t)(it / S) & 1u;
-      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
+      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride, (p.dbg & 32) != 0};
       const int n0 = n_blk * block_n;
       int width = p.N - n0; if (width > block_n) width = block_n;
-      tc_epilogue<EPI, (S == 2)>(p, acc, st, &tmO0, &tmO1, m_blk * kBlockM + q * 32, lane, n0, width,
+      if (p.dbg & 64) { ptx::mbar_wait(tfull + grp, aphase); ptx::tc_fence_after(); }   // tuning experiments: empty epilogue
+      else
+      tc_epilogue<EPI, (S == 2 ? 1 : 0)>(p, acc, st, &tmO0, &tmO1, m_blk * kBlockM + q * 32, lane, n0, width,
                        [&]() { ptx::mbar_wait(tfull + grp, aphase); ptx::tc_fence_after(); });
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty + grp);
     }
     st.acquire();   // the staging buffers must outlive every store that reads them
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------
+// A-resident variant for wide outputs with a short reduction (K <= 256: q|k|v, gated up-projection, d(gate)):
+// a CTA owns whole 128-row blocks, loads the A block ONCE into shared memory and streams only the weight tiles
+// through the ring while it walks the output tiles of that block -- roughly half the L2->SM operand traffic
+// (and bytes in flight per tile) of the generic kernel, which re-fetches A for every output tile.
+// ---------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(64 + 128 * 4, 1)
+gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, GemmArgs p,
+                    int block_n, int stages, int n_blks, int m_blks) {
+  constexpr int S = 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  constexpr uint32_t kAccStride = 512 / S;
+  constexpr uint32_t kStagingBytes = 4 * S * kStageBufBytes;   // one box per epilogue warp
+
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const uint32_t a_bytes = (uint32_t)num_kb * kATileBytes;
+  const uint32_t b_bytes = (uint32_t)block_n * 128u;
+  uint8_t* a_res = smem;
+  uint8_t* ring = a_res + a_bytes;
+  uint8_t* staging = ring + (size_t)stages * b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint64_t* tempty = tfull + S;
+  uint64_t* a_full = tempty + S;
+  uint64_t* a_empty = a_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmO0); ptx::prefetch_tmap(&tmO1);
+    for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weight tiles stream continuously (they do not depend on the resident A block)
+      int stage = 0; uint32_t phase = 0;
+      for (int mb = blockIdx.x; mb < m_blks; mb += gridDim.x)
+        for (int nb = 0; nb < n_blks; ++nb)
+          for (int kb = 0; kb < num_kb; ++kb) {
+            ptx::mbar_wait(empty + stage, phase ^ 1u);
+            ptx::mbar_expect_tx(full + stage, b_bytes);
+            ptx::tma_load_2d(ring + (size_t)stage * b_bytes, &tmB, full + stage, kb * kBlockK, nb * block_n);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(block_n, false, false);
+      int stage = 0; uint32_t phase = 0, aph = 0;
+      int it = 0;
+      for (int mb = blockIdx.x; mb < m_blks; mb += gridDim.x) {
+        // the MMA thread owns the resident A block: it reloads it once every MMA that read the previous block has retired
+        if (aph != 0u || mb != (int)blockIdx.x) ptx::mbar_wait(a_empty, aph ^ 1u);
+        ptx::mbar_expect_tx(a_full, a_bytes);
+        for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(a_res + (size_t)kb * kATileBytes, &tmA, a_full, kb * kBlockK, mb * kBlockM);
+        ptx::mbar_wait(a_full, aph);
+        for (int nb = 0; nb < n_blks; ++nb, ++it) {
+          const int as = it % S;
+          ptx::mbar_wait(tempty + as, ((uint32_t)(it / S) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)as * kAccStride;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            ptx::mbar_wait(full + stage, phase);
+            ptx::tc_fence_after();
+            const uint64_t adesc = make_smem_desc(ptx::smem_u32(a_res + (size_t)kb * kATileBytes), 16, 1024);
+            const uint64_t bdesc = make_smem_desc(ptx::smem_u32(ring + (size_t)stage * b_bytes), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit(empty + stage);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+          ptx::umma_commit(tfull + as);
+        }
+        ptx::umma_commit(a_empty);
+        aph ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * kStageBufBytes, lane, false, 0};
+    const int my_blocks = blockIdx.x < m_blks ? (m_blks - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int my_tiles = my_blocks * n_blks;
+    for (int it = grp; it < my_tiles; it += S) {
+      const int mb = blockIdx.x + (it / n_blks) * gridDim.x, nb = it % n_blks;
+      const uint32_t aphase = (uint32_t)(it / S) & 1u;
+      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
+      const int n0 = nb * block_n;
+      int width = p.N - n0; if (width > block_n) width = block_n;
+      tc_epilogue<EPI, 2>(p, acc, st, &tmO0, &tmO1, mb * kBlockM + q * 32, lane, n0, width,
+                          [&]() { ptx::mbar_wait(tfull + grp, aphase); ptx::tc_fence_after(); });
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty + grp);
+    }
+    st.acquire();
   }
 
   ptx::tc_fence_before();
@@ -819,6 +960,34 @@ int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_b
 }
 
 template <int EPI>
+int launch_gemm_ares(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int m_blks, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_ares_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    configured = true;
+  }
+  const int num_kb = ceil_div(a.K, kBlockK);
+  const int fixed = num_kb * kATileBytes + 16 * kStageBufBytes + 2048;
+  // d(gate) reads its saved pre-activations row-wise through L1: keep ~36 KB of the array as cache
+  const int cap = (EPI == kEpiDSwiGLU) ? kSmemMax - 36 * 1024 : kSmemMax;
+  int stages = (cap - fixed) / (block_n * 128);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const size_t smem = (size_t)fixed + (size_t)stages * block_n * 128;
+  HS_REQUIRE(smem <= (size_t)kSmemMax, "gemm(A-resident): %zu bytes of shared memory", smem);
+  const int grid = m_blks < kNumSMs ? m_blks : kNumSMs;
+  gemm_tc_ares_kernel<EPI><<<grid, 64 + 128 * 4, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], a, block_n, stages, n_blks, m_blks);
+  HS_CHECK_LAUNCH("gemm_tc_ares_kernel");
+  return kOk;
+}
+
+// wide output + short reduction: keep the A block resident (HSIMAE_GEMM_ARES=0 disables, for A/B measurements)
+bool use_ares(const GemmArgs& a, int epi, int block_n, int n_blks) {
+  static const bool enabled = !(getenv("HSIMAE_GEMM_ARES") && atoi(getenv("HSIMAE_GEMM_ARES")) == 0);
+  return enabled && n_blks >= 2 && block_n <= 128 && a.K <= 256 && (epi == kEpiBiasBf16 || epi == kEpiSwiGLU || epi == kEpiDSwiGLU);
+}
+
+template <int EPI>
 int launch_gemm(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int num_tiles, cudaStream_t stream) {
   // as many accumulator stages (= epilogue warp groups) as fit in the 512 TMEM columns
   if (block_n <= 128) return launch_gemm_s<EPI, 4>(a, tm, block_n, n_blks, num_tiles, stream);
@@ -871,6 +1040,7 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
     case kEpiBiasBf16:
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
       tm[3] = tm[2];
+      if (use_ares(a, epi, block_n, n_blks)) return launch_gemm_ares<kEpiBiasBf16>(a, tm, block_n, n_blks, m_blks, stream);
       return launch_gemm<kEpiBiasBf16>(a, tm, block_n, n_blks, num_tiles, stream);
     case kEpiBiasF32:
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 32, 32, &tm[2], 4));
@@ -884,10 +1054,12 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
     case kEpiSwiGLU:
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
       HS_TRY(get_tmap(a.out1, N / 2, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
+      if (use_ares(a, epi, block_n, n_blks)) return launch_gemm_ares<kEpiSwiGLU>(a, tm, block_n, n_blks, m_blks, stream);
       return launch_gemm<kEpiSwiGLU>(a, tm, block_n, n_blks, num_tiles, stream);
     case kEpiDSwiGLU:
       HS_TRY(get_tmap(a.out0, 2 * N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
       tm[3] = tm[2];
+      if (use_ares(a, epi, block_n, n_blks)) return launch_gemm_ares<kEpiDSwiGLU>(a, tm, block_n, n_blks, m_blks, stream);
       return launch_gemm<kEpiDSwiGLU>(a, tm, block_n, n_blks, num_tiles, stream);
   }
   set_error("gemm: bad epilogue %d", epi);
