@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("HSIMAE_NVCC_EXTRA", "").split()   # e.g. -DHSIMAE_TRACE (tuning instrument, see csrc/gemm_tc.cu)
 
 
 def _nvcc() -> str:

@@ -849,7 +849,6 @@ int hsimae_gemm(const hsimae_gemm_desc* d, void* stream) {
   a.resid2 = d->resid2; a.gamma = d->gamma; a.beta = d->beta; a.stats = d->stats; a.ab = (const bf16*)d->ab; a.ldab = d->ldab;
   a.rs.scale = d->rowscale; a.rs.mode = d->rs_mode; a.rs.K = d->rs_K > 0 ? d->rs_K : 1; a.rs.len_l = d->rs_len_l > 0 ? d->rs_len_l : 1; a.rs.G = d->rs_G;
   a.ln_eps = 1e-5f;
-  a.dbg = getenv("HSIMAE_GEMM_DBG") ? atoi(getenv("HSIMAE_GEMM_DBG")) : 0;   // single-operator ABI only (tuning experiments)
   if (d->impl == 1) return gemm_simt(a, d->epilogue, d->scratch, (cudaStream_t)stream);
   return gemm_tc(a, d->epilogue, (cudaStream_t)stream);
 }

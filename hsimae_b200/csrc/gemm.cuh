@@ -36,7 +36,6 @@ struct GemmArgs {
   float* stats;                        // [M,2] (mean, rstd) or nullptr
   const __nv_bfloat16* ab; int ldab;   // kEpiDSwiGLU: saved pre-activations (interleaved)
   float ln_eps;
-  int dbg;                             // tuning experiments only: 1 = skip output stores, 4 = skip MMAs, 8 = skip operand loads
 };
 
 struct WgradArgs {

@@ -22,6 +22,19 @@
 
 namespace hsimae {
 
+// Build with -DHSIMAE_TRACE to accumulate, per CTA and warp role, the cycles spent in each pipeline wait
+// (read back with hsimae_debug_trace; tuning instrument, not part of the product build).
+#ifdef HSIMAE_TRACE
+__device__ long long g_trace[256 * 16];
+#define TR_DECL long long tr_t0 = clock64(), tr_acc[3] = {0, 0, 0}
+#define TR_WAIT(i, ...) { long long tr_t = clock64(); __VA_ARGS__; tr_acc[i] += clock64() - tr_t; }
+#define TR_DUMP(slot) { long long* tr_o = g_trace + blockIdx.x * 16 + (slot) * 4; tr_o[0] = clock64() - tr_t0; tr_o[1] = tr_acc[0]; tr_o[2] = tr_acc[1]; tr_o[3] = tr_acc[2]; }
+#else
+#define TR_DECL
+#define TR_WAIT(i, ...) { __VA_ARGS__; }
+#define TR_DUMP(slot)
+#endif
+
 // ---------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------
@@ -76,6 +89,56 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: two CTAs of a cluster on one TPC drive ONE 256-row MMA; each loads its own
+// 128 A rows and HALF of the B tile, the tensor core reads both shared memories.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// load into THIS CTA's shared memory, completion bytes signalled on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+// pull `bytes` (multiple of 16) starting at a 16-byte aligned global address into L2, asynchronously
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// silu(a) = a * sigmoid(a) with sigmoid(a) = 0.5 + 0.5 tanh(a / 2): one MUFU op instead of exp + reciprocal
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float a) { return fmaf(tanh_approx(0.5f * a), 0.5f, 0.5f); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -153,13 +216,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // accumulator row of this thread in TMEM (lane = row, column = n)
 struct TmemAcc {
   uint32_t base;  // (lane_base << 16) | column_base
-  bool skip = false;   // tuning experiments only
   template <int W> __device__ __forceinline__ void load(int c, float (&v)[W]) {
-    if (skip) {
-#pragma unroll
-      for (int i = 0; i < W; ++i) v[i] = 1.0f;
-      return;
-    }
     if constexpr (W == 32) ptx::tmem_ld32(base + c, v); else ptx::tmem_ld16(base + c, v);
     ptx::tmem_ld_wait();
   }
@@ -186,9 +243,6 @@ struct Stager {
   uint32_t base;     // smem address of this warp's two 4 KB buffers (1024-byte aligned)
   int lane;
   bool pending;      // a committed store may still be reading the buffers
-  int cur = 0;       // (unused)
-  bool mute = false; // tuning experiments: do not issue the stores
-  bool nofence = false;
   // wait until the TMA unit has finished reading every box this warp handed over
   __device__ __forceinline__ void acquire() {
     if (pending) {
@@ -205,9 +259,9 @@ struct Stager {
     ptx::st_shared_v4(base + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v);
   }
   __device__ __forceinline__ void flush(int b, const CUtensorMap* tm, int col, int row) {
-    if (!nofence) ptx::fence_proxy_async();
+    ptx::fence_proxy_async();
     __syncwarp();
-    if (lane == 0 && !mute) { ptx::tma_store_2d(tm, base + (uint32_t)b * kStageBufBytes, col, row); ptx::bulk_commit(); }
+    if (lane == 0) { ptx::tma_store_2d(tm, base + (uint32_t)b * kStageBufBytes, col, row); ptx::bulk_commit(); }
     pending = true;
   }
 };
@@ -269,7 +323,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float a = bf16_round(v[i]), b = bf16_round(v[16 + i]);   // gate on what backward will re-read
-        g[i] = silu_f(a) * b;
+        g[i] = a * ptx::sigmoid_fast(a) * b;
       }
       if ((c & 63) == 0) st.acquire();
       const int j0 = (c & 63) >> 3;
@@ -289,6 +343,8 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
     // tile of hidden columns; every 16 of them become 32 packed output columns.  The saved pre-activations of the
     // NEXT chunk are fetched while the current one is being processed (the first fetch overlaps the MMA tail).
     const __nv_bfloat16* abrow = p.ab + (size_t)(valid ? m : 0) * p.ldab + 2 * n0;
+    // the tile's saved pre-activations start moving HBM -> L2 while the MMAs of the tile are still running
+    if (valid) ptx::prefetch_l2_bulk(abrow, (uint32_t)width * 4u);
     uint4 nxt[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) nxt[i] = valid ? *reinterpret_cast<const uint4*>(abrow + 8 * i) : make_uint4(0u, 0u, 0u, 0u);  // L1-allocating: the 4 loads share one line
@@ -313,7 +369,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float a = ab[i], b = ab[16 + i];
-        const float sg = __fdividef(1.0f, 1.0f + __expf(-a));
+        const float sg = ptx::sigmoid_fast(a);
         o[i] = dg[i] * b * (sg * (1.0f + a * (1.0f - sg)));
         o[16 + i] = dg[i] * (a * sg);
       }
@@ -418,7 +474,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // Instruction descriptor for kind::f16, bf16 x bf16 -> f32, M=128.
-__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major, int m = 128) {
   uint32_t d = 0;
   d |= 1u << 4;                       // accumulator format f32
   d |= 1u << 7;                       // A = bf16
@@ -426,7 +482,7 @@ __host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
   d |= (a_mn_major ? 1u : 0u) << 15;  // A major
   d |= (b_mn_major ? 1u : 0u) << 16;  // B major
   d |= (uint32_t)(n >> 3) << 17;      // N / 8
-  d |= (uint32_t)(128 >> 4) << 24;    // M / 16
+  d |= (uint32_t)(m >> 4) << 24;      // M / 16 (256: both CTAs of a pair)
   return d;
 }
 
@@ -446,7 +502,13 @@ constexpr int kSmemBudget = 200 * 1024;
 // are being drained concurrently (S warps per scheduler hide each other's
 // TMEM / global latency) while the MMA warp fills the next free stage.
 // ---------------------------------------------------------------------------
-template <int EPI, int S>
+// P = 2: CTA-pair mode.  The two CTAs of a cluster own consecutive 128-row blocks; each loads its own A rows and HALF
+// of the weight tile, the leader (cluster rank 0) issues 256-row cta_group::2 MMAs that read both shared memories and
+// write 128 accumulator rows into each CTA's TMEM.  Weight bytes fetched from L2 per output row are halved -- these
+// kernels run at the L2 slice throughput cap (~12 TB/s of SM<->L2 sectors), not at the HBM or tensor roofline.
+// Barrier ownership: `full` lives in the leader (both producers' TMA bytes land on it), `empty` / `tfull` are
+// signalled in both CTAs by multicast tcgen05.commit, `tempty` lives in the leader (both CTAs' epilogues arrive).
+template <int EPI, int S, int P>
 __global__ void __launch_bounds__(64 + 128 * S, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, GemmArgs p,
@@ -457,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t kAccStride = 512 / S;
   constexpr uint32_t kStagingBytes = 4 * S * StagingBufs<EPI>::value * kStageBufBytes;
 
-  const uint32_t b_bytes = (uint32_t)block_n * 128u;
+  const uint32_t b_bytes = (uint32_t)(block_n / P) * 128u;   // this CTA's share of the weight tile
   const uint32_t stage_bytes = kATileBytes + b_bytes;
   uint8_t* staging = smem + (size_t)stages * stage_bytes;   // 1024-byte aligned (stage_bytes is a multiple of 1024)
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
@@ -469,6 +531,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int crank = P == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / P, unit_step = (int)gridDim.x / P;   // a "unit" walks tiles of 128*P rows
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -476,137 +540,163 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmO0);
     ptx::prefetch_tmap(&tmO1);
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128 * P); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (P == 2) ptx::cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      TR_DECL;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
+        const int m0 = (m_blk * P + crank) * kBlockM;
+        const int n0 = n_blk * block_n + crank * (block_n / P);
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(empty + stage, phase ^ 1u);
+          TR_WAIT(0, ptx::mbar_wait(empty + stage, phase ^ 1u));
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          if (p.dbg & 8) { ptx::mbar_arrive(full + stage); }
-          else {
-          ptx::mbar_expect_tx(full + stage, stage_bytes);
-          ptx::tma_load_2d(sa, &tmA, full + stage, kb * kBlockK, m_blk * kBlockM);
-          ptx::tma_load_2d(sa + kATileBytes, &tmB, full + stage, kb * kBlockK, n_blk * block_n);
+          if constexpr (P == 2) {
+            if (crank == 0) ptx::mbar_expect_tx(full + stage, 2u * stage_bytes);
+            const uint32_t bar = ptx::mapa_rank(ptx::smem_u32(full + stage), 0);
+            ptx::tma_load_2d_pair(sa, &tmA, bar, kb * kBlockK, m0);
+            ptx::tma_load_2d_pair(sa + kATileBytes, &tmB, bar, kb * kBlockK, n0);
+          } else {
+            ptx::mbar_expect_tx(full + stage, stage_bytes);
+            ptx::tma_load_2d(sa, &tmA, full + stage, kb * kBlockK, m0);
+            ptx::tma_load_2d(sa + kATileBytes, &tmB, full + stage, kb * kBlockK, n0);
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
+      TR_DUMP(0);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(block_n, false, false);
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = make_idesc(block_n, false, false, kBlockM * P);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      TR_DECL;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
         const int as = it % S;
         const uint32_t aphase = (uint32_t)(it / S) & 1u;
-        ptx::mbar_wait(tempty + as, aphase ^ 1u);
+        TR_WAIT(1, ptx::mbar_wait(tempty + as, aphase ^ 1u));
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(full + stage, phase);
+          TR_WAIT(2, ptx::mbar_wait(full + stage, phase));
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sa + kATileBytes, 16, 1024);
-          if (!(p.dbg & 4)) {
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 K-elements = 32 bytes inside the 128B swizzle row
-            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (P == 2) ptx::umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            else ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          }
-          ptx::umma_commit(empty + stage);
+          if constexpr (P == 2) ptx::umma_commit_pair(empty + stage); else ptx::umma_commit(empty + stage);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull + as);
+        if constexpr (P == 2) ptx::umma_commit_pair(tfull + as); else ptx::umma_commit(tfull + as);
       }
+      TR_DUMP(1);
     }
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;   // accumulator stage served by this warp's group
-    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI>::value * kStageBufBytes), lane, false, 0, (p.dbg & 1) != 0, (p.dbg & 16) != 0};
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI>::value * kStageBufBytes), lane, false};
+    const uint32_t tempty_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(tempty + grp), 0) : 0u;
     int it = grp;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += S * gridDim.x, it += S) {
+    TR_DECL;
+    for (int tile = unit0 + grp * unit_step; tile < num_tiles; tile += S * unit_step, it += S) {
       const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
       const uint32_t aphase = (uint32_t)(it / S) & 1u;
-      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride, (p.dbg & 32) != 0};
+      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
       const int n0 = n_blk * block_n;
       int width = p.N - n0; if (width > block_n) width = block_n;
-      if (p.dbg & 64) { ptx::mbar_wait(tfull + grp, aphase); ptx::tc_fence_after(); }   // tuning experiments: empty epilogue
-      else
-      tc_epilogue<EPI, (S == 2 ? 1 : 0)>(p, acc, st, &tmO0, &tmO1, m_blk * kBlockM + q * 32, lane, n0, width,
-                       [&]() { ptx::mbar_wait(tfull + grp, aphase); ptx::tc_fence_after(); });
+      TR_WAIT(1, tc_epilogue<EPI, (S == 2 ? 1 : 0)>(p, acc, st, &tmO0, &tmO1, (m_blk * P + crank) * kBlockM + q * 32, lane, n0, width,
+                       [&]() { TR_WAIT(0, ptx::mbar_wait(tfull + grp, aphase)); ptx::tc_fence_after(); }));
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty + grp);
+      if constexpr (P == 2) ptx::mbar_arrive_cluster(tempty_addr); else ptx::mbar_arrive(tempty + grp);
     }
     st.acquire();   // the staging buffers must outlive every store that reads them
+    if (warp == 2 && lane == 0) TR_DUMP(2);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+  if constexpr (P == 2) ptx::cluster_sync_all();   // nobody leaves while the peer may still read its shared memory / barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (P == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------
 // A-resident variant for wide outputs with a short reduction (K <= 256: q|k|v, gated up-projection, d(gate)):
 // a CTA owns whole 128-row blocks, loads the A block ONCE into shared memory and streams only the weight tiles
-// through the ring while it walks the output tiles of that block -- roughly half the L2->SM operand traffic
-// (and bytes in flight per tile) of the generic kernel, which re-fetches A for every output tile.
+// through the ring while it walks the output tiles of that block -- the generic kernel re-fetches A for every
+// output tile.  P = 2 is the CTA-pair mode described above (each CTA streams half of every weight tile).
 // ---------------------------------------------------------------------------
-template <int EPI>
+// The MMA tile is up to 256 columns wide (one instruction stream per FLOP is what limits these short-K GEMMs: the
+// single issuing thread needs ~400-600 cycles per 64-deep k-block for waits, descriptors and commits, so each k-block
+// must carry >= 512 tensor-cycles of work).  Accumulators wider than 128 columns are drained by TWO epilogue groups,
+// one per 128-column half, so all four groups stay busy: H = halves per tile, S = 4 / H accumulator stages.
+template <int EPI, int P>
 __global__ void __launch_bounds__(64 + 128 * 4, 1)
 gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, GemmArgs p,
-                    int block_n, int stages, int n_blks, int m_blks) {
-  constexpr int S = 4;
+                    int block_n, int stages, int n_blks, int m_units) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  constexpr uint32_t kAccStride = 512 / S;
-  constexpr uint32_t kStagingBytes = 4 * S * kStageBufBytes;   // one box per epilogue warp
+  constexpr uint32_t kStagingBytes = 16 * kStageBufBytes;   // one box per epilogue warp
+  const int H = block_n > 128 ? 2 : 1;
+  const int S = 4 / H;
+  const uint32_t acc_stride = 128u * (uint32_t)H;
 
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
   const uint32_t a_bytes = (uint32_t)num_kb * kATileBytes;
-  const uint32_t b_bytes = (uint32_t)block_n * 128u;
+  const uint32_t b_bytes = (uint32_t)(block_n / P) * 128u;
   uint8_t* a_res = smem;
   uint8_t* ring = a_res + a_bytes;
   uint8_t* staging = ring + (size_t)stages * b_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
-  uint64_t* tempty = tfull + S;
-  uint64_t* a_full = tempty + S;
+  uint64_t* tempty = tfull + 4;
+  uint64_t* a_full = tempty + 4;
   uint64_t* a_empty = a_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int crank = P == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / P, unit_step = (int)gridDim.x / P;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmO0); ptx::prefetch_tmap(&tmO1);
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128 * H * P); }
     ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (P == 2) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -614,71 +704,117 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       // weight tiles stream continuously (they do not depend on the resident A block)
       int stage = 0; uint32_t phase = 0;
-      for (int mb = blockIdx.x; mb < m_blks; mb += gridDim.x)
+      TR_DECL;
+      for (int mu = unit0; mu < m_units; mu += unit_step)
         for (int nb = 0; nb < n_blks; ++nb)
           for (int kb = 0; kb < num_kb; ++kb) {
-            ptx::mbar_wait(empty + stage, phase ^ 1u);
-            ptx::mbar_expect_tx(full + stage, b_bytes);
-            ptx::tma_load_2d(ring + (size_t)stage * b_bytes, &tmB, full + stage, kb * kBlockK, nb * block_n);
+            TR_WAIT(0, ptx::mbar_wait(empty + stage, phase ^ 1u));
+            if constexpr (P == 2) {
+              if (crank == 0) ptx::mbar_expect_tx(full + stage, 2u * b_bytes);
+              ptx::tma_load_2d_pair(ring + (size_t)stage * b_bytes, &tmB, ptx::mapa_rank(ptx::smem_u32(full + stage), 0), kb * kBlockK,
+                                    nb * block_n + crank * (block_n / P));
+            } else {
+              ptx::mbar_expect_tx(full + stage, b_bytes);
+              ptx::tma_load_2d(ring + (size_t)stage * b_bytes, &tmB, full + stage, kb * kBlockK, nb * block_n);
+            }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
+      TR_DUMP(0);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(block_n, false, false);
-      int stage = 0; uint32_t phase = 0, aph = 0;
-      int it = 0;
-      for (int mb = blockIdx.x; mb < m_blks; mb += gridDim.x) {
-        // the MMA thread owns the resident A block: it reloads it once every MMA that read the previous block has retired
-        if (aph != 0u || mb != (int)blockIdx.x) ptx::mbar_wait(a_empty, aph ^ 1u);
-        ptx::mbar_expect_tx(a_full, a_bytes);
-        for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(a_res + (size_t)kb * kATileBytes, &tmA, a_full, kb * kBlockK, mb * kBlockM);
-        ptx::mbar_wait(a_full, aph);
+    // The whole warp walks this loop (uniform control flow keeps counters and descriptors in uniform registers); lane 0
+    // issues.  It owns the resident A block of its CTA: reloaded once every MMA that read the previous block has retired
+    // (a_empty, signalled in both CTAs of a pair); the leader CTA also issues the MMAs.
+    const uint32_t idesc = make_idesc(block_n, false, false, kBlockM * P);
+    const uint32_t a_full_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(a_full), 0) : 0u;
+    const uint64_t adesc0 = make_smem_desc(ptx::smem_u32(a_res), 16, 1024);
+    const uint64_t bdesc0 = make_smem_desc(ptx::smem_u32(ring), 16, 1024);
+    const uint32_t b_units = b_bytes >> 4;
+    int stage = 0; uint32_t phase = 0, aph = 0;
+    int it = 0;
+    TR_DECL;
+    for (int mu = unit0; mu < m_units; mu += unit_step) {
+      const int m0 = (mu * P + crank) * kBlockM;   // may lie past the last row: TMA zero-fills the load and clips the stores
+      if (mu != unit0) ptx::mbar_wait(a_empty, aph ^ 1u);
+      if (lane == 0) {
+        if constexpr (P == 2) {
+          if (crank == 0) ptx::mbar_expect_tx(a_full, 2u * a_bytes);
+          for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d_pair(a_res + (size_t)kb * kATileBytes, &tmA, a_full_addr, kb * kBlockK, m0);
+        } else {
+          ptx::mbar_expect_tx(a_full, a_bytes);
+          for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(a_res + (size_t)kb * kATileBytes, &tmA, a_full, kb * kBlockK, m0);
+        }
+      }
+      __syncwarp();
+      if (crank == 0) {
+        TR_WAIT(0, ptx::mbar_wait(a_full, aph));
         for (int nb = 0; nb < n_blks; ++nb, ++it) {
           const int as = it % S;
-          ptx::mbar_wait(tempty + as, ((uint32_t)(it / S) & 1u) ^ 1u);
+          TR_WAIT(1, ptx::mbar_wait(tempty + as, ((uint32_t)(it / S) & 1u) ^ 1u));
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)as * kAccStride;
+          const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_stride;
           for (int kb = 0; kb < num_kb; ++kb) {
-            ptx::mbar_wait(full + stage, phase);
+            TR_WAIT(2, ptx::mbar_wait(full + stage, phase));
             ptx::tc_fence_after();
-            const uint64_t adesc = make_smem_desc(ptx::smem_u32(a_res + (size_t)kb * kATileBytes), 16, 1024);
-            const uint64_t bdesc = make_smem_desc(ptx::smem_u32(ring + (size_t)stage * b_bytes), 16, 1024);
+            if (lane == 0) {
+              const uint64_t adesc = adesc0 + (uint64_t)(kb * (kATileBytes >> 4));
+              const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)stage * b_units);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-            ptx::umma_commit(empty + stage);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if constexpr (P == 2) ptx::umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                else ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              if constexpr (P == 2) ptx::umma_commit_pair(empty + stage); else ptx::umma_commit(empty + stage);
+              if (kb == num_kb - 1) {
+                if constexpr (P == 2) ptx::umma_commit_pair(tfull + as); else ptx::umma_commit(tfull + as);
+              }
+            }
+            __syncwarp();
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
-          ptx::umma_commit(tfull + as);
         }
-        ptx::umma_commit(a_empty);
-        aph ^= 1u;
+        if (lane == 0) { if constexpr (P == 2) ptx::umma_commit_pair(a_empty); else ptx::umma_commit(a_empty); }
+        __syncwarp();
       }
+      aph ^= 1u;
     }
+    if (lane == 0) TR_DUMP(1);
   } else {
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
-    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * kStageBufBytes, lane, false, 0};
-    const int my_blocks = blockIdx.x < m_blks ? (m_blks - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    const int my_tiles = my_blocks * n_blks;
-    for (int it = grp; it < my_tiles; it += S) {
-      const int mb = blockIdx.x + (it / n_blks) * gridDim.x, nb = it % n_blks;
+    const int as = grp / H, half = grp % H;     // accumulator stage and 128-column half served by this group
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * kStageBufBytes, lane, false};
+    const uint32_t tempty_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(tempty + as), 0) : 0u;
+    const int my_units = unit0 < m_units ? (m_units - 1 - unit0) / unit_step + 1 : 0;
+    const int my_tiles = my_units * n_blks;
+    TR_DECL;
+    for (int it = as; it < my_tiles; it += S) {
+      const int mu = unit0 + (it / n_blks) * unit_step, nb = it % n_blks;
       const uint32_t aphase = (uint32_t)(it / S) & 1u;
-      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
-      const int n0 = nb * block_n;
-      int width = p.N - n0; if (width > block_n) width = block_n;
-      tc_epilogue<EPI, 2>(p, acc, st, &tmO0, &tmO1, mb * kBlockM + q * 32, lane, n0, width,
-                          [&]() { ptx::mbar_wait(tfull + grp, aphase); ptx::tc_fence_after(); });
+      TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * acc_stride + (uint32_t)half * 128u};
+      const int n0 = nb * block_n + half * 128;
+      int width = p.N - n0; if (width > 128) width = 128;
+      if (width > block_n) width = block_n;
+      auto wait_acc = [&]() { TR_WAIT(0, ptx::mbar_wait(tfull + as, aphase)); ptx::tc_fence_after(); };
+      if (width > 0) {
+        TR_WAIT(1, tc_epilogue<EPI, 2>(p, acc, st, &tmO0, &tmO1, (mu * P + crank) * kBlockM + q * 32, lane, n0, width, wait_acc));
+      } else {
+        wait_acc();   // nothing to drain in this half, but the stage is only free once the tile's MMAs have retired
+      }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty + grp);
+      if constexpr (P == 2) ptx::mbar_arrive_cluster(tempty_addr); else ptx::mbar_arrive(tempty + as);
     }
     st.acquire();
+    if (warp == 2 && lane == 0) TR_DUMP(2);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+  if constexpr (P == 2) ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (P == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -690,6 +826,9 @@ constexpr int kOnesBytes = 16 * 1024;  // all-ones B operand for the fused colum
 // Bias gradients ride along: dbias[n] = sum_m Y[m,n] * 1 is one more MMA per K-step against an all-ones
 // B tile (N = 16) that lives in shared memory for the whole kernel -- a tile of ones is the same in every
 // swizzle/major layout -- accumulated in 16 extra TMEM columns.  Only the c_blk == 0 tiles do it.
+// P = 2: a CTA pair owns 256 output rows x bn columns of one reduction split; each CTA loads the Y box of its own 128
+// output rows and HALF of the X columns (the operand that every row tile re-reads), the leader issues 256-row MMAs.
+template <int P>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, WgradArgs p,
                 int bn, int stages, int tiles_c, int num_tiles, int kb_total, int kb_per_split,
@@ -698,8 +837,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
 
+  const int bn_cta = bn / P;                                    // X columns staged by this CTA
   const uint32_t a_bytes = 2 * kBoxBytes;
-  const uint32_t b_bytes = (uint32_t)(bn / 64) * kBoxBytes;
+  const uint32_t b_bytes = (uint32_t)(bn_cta / 64) * kBoxBytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* ones = smem + (size_t)stages * stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(ones + kOnesBytes);
@@ -709,9 +849,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x % num_tiles;
-  const int split = blockIdx.x / num_tiles;
+  const int crank = P == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int unit = (int)blockIdx.x / P;
+  const int tile = unit % num_tiles;
+  const int split = unit / num_tiles;
   const int r_blk = tile / tiles_c, c_blk = tile - r_blk * tiles_c;
+  const int row0 = (r_blk * P + crank) * kBlockM;               // first output row of this CTA
   const int kb0 = split * kb_per_split;
   int kb1 = kb0 + kb_per_split; if (kb1 > kb_total) kb1 = kb_total;
   const int nkb = kb1 - kb0;
@@ -728,9 +871,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     ptx::mbar_init(tfull, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (P == 2) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -741,18 +888,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty + stage, phase ^ 1u);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          ptx::mbar_expect_tx(full + stage, stage_bytes);
-          for (int j = 0; j < 2; ++j)
-            ptx::tma_load_2d(sa + j * kBoxBytes, &tmY, full + stage, r_blk * kBlockM + j * 64, kb * 64);
-          for (int j = 0; j < bn / 64; ++j)
-            ptx::tma_load_2d(sa + a_bytes + j * kBoxBytes, &tmX, full + stage, c_blk * bn + j * 64, kb * 64);
+          if constexpr (P == 2) {
+            if (crank == 0) ptx::mbar_expect_tx(full + stage, 2u * stage_bytes);
+            const uint32_t bar = ptx::mapa_rank(ptx::smem_u32(full + stage), 0);
+            for (int j = 0; j < 2; ++j) ptx::tma_load_2d_pair(sa + j * kBoxBytes, &tmY, bar, row0 + j * 64, kb * 64);
+            for (int j = 0; j < bn_cta / 64; ++j)
+              ptx::tma_load_2d_pair(sa + a_bytes + j * kBoxBytes, &tmX, bar, c_blk * bn + crank * bn_cta + j * 64, kb * 64);
+          } else {
+            ptx::mbar_expect_tx(full + stage, stage_bytes);
+            for (int j = 0; j < 2; ++j) ptx::tma_load_2d(sa + j * kBoxBytes, &tmY, full + stage, row0 + j * 64, kb * 64);
+            for (int j = 0; j < bn / 64; ++j)
+              ptx::tma_load_2d(sa + a_bytes + j * kBoxBytes, &tmX, full + stage, c_blk * bn + j * 64, kb * 64);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc(bn, true, true);
-        const uint32_t idesc_ones = make_idesc(16, true, true);
+      if (lane == 0 && crank == 0) {
+        const uint32_t idesc = make_idesc(bn, true, true, kBlockM * P);
+        const uint32_t idesc_ones = make_idesc(16, true, true, kBlockM * P);
         const uint64_t ones_desc = make_smem_desc(ptx::smem_u32(ones), lbo, sbo);
         int stage = 0; uint32_t phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -763,20 +917,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           for (int k = 0; k < 4; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * kstep_bytes, lbo, sbo);
             const uint64_t bdesc = make_smem_desc(sa + a_bytes + k * kstep_bytes, lbo, sbo);
-            ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (do_bias) ptx::umma_bf16(tmem_base + 256, adesc, ones_desc, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (P == 2) {
+              ptx::umma_bf16_pair(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (do_bias) ptx::umma_bf16_pair(tmem_base + 256, adesc, ones_desc, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+            } else {
+              ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (do_bias) ptx::umma_bf16(tmem_base + 256, adesc, ones_desc, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          ptx::umma_commit(empty + stage);
+          if constexpr (P == 2) ptx::umma_commit_pair(empty + stage); else ptx::umma_commit(empty + stage);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull);
+        if constexpr (P == 2) ptx::umma_commit_pair(tfull); else ptx::umma_commit(tfull);
       }
     } else {
       const int q = warp & 3;
       ptx::mbar_wait(tfull, 0);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int r = r_blk * kBlockM + q * 32 + lane;  // packed output row
+      const int r = row0 + q * 32 + lane;  // packed output row
       float* drow = nullptr;
       float* brow = nullptr;
       if (r < p.Nout) {
@@ -813,7 +972,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+  if constexpr (P == 2) ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (P == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -931,16 +1094,36 @@ int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t
 
 constexpr int kSmemMax = 227 * 1024;
 
-template <int EPI, int S>
-int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int num_tiles, cudaStream_t stream) {
+// launches on `grid` CTAs, as clusters of P
+template <class Kernel, class... Args>
+int launch_clustered(Kernel kernel, int grid, int threads, size_t smem, int P, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  HS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+  return kOk;
+}
+
+// grid for `units` work items of P CTAs each: at most one CTA per SM, whole clusters
+int pair_grid(int units, int P) {
+  int g = units * P;
+  if (g > kNumSMs) g = kNumSMs / P * P;
+  return g;
+}
+
+template <int EPI, int S, int P>
+int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int m_blks, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
   // shared memory: [operand pipeline stages][epilogue staging boxes][barriers]; as many stages as fit
   const int staging = 4 * S * StagingBufs<EPI>::value * kStageBufBytes;
-  const int stage_bytes = kATileBytes + block_n * 128;
+  const int stage_bytes = kATileBytes + block_n / P * 128;
   const int num_kb = ceil_div(a.K, kBlockK);
   // epilogues that read per-row global inputs (saved pre-activations, residual) rely on L1 to merge each thread's
   // 16-byte loads of one line: leave ~36 KB of the 228 KB shared/L1 array to the cache for them
@@ -948,35 +1131,36 @@ int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_b
   int stages = (smem_cap - staging - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > 2 * num_kb) stages = 2 * num_kb;
-  static const int stage_cap = getenv("HSIMAE_GEMM_STAGES") ? atoi(getenv("HSIMAE_GEMM_STAGES")) : 0;   // tuning experiments
-  if (stage_cap > 0 && stages > stage_cap) stages = stage_cap;
   if (stages < 2) stages = 2;
   const size_t smem = (size_t)stages * stage_bytes + staging + 1024 + 512;
   HS_REQUIRE(smem <= (size_t)kSmemMax, "gemm: tile N=%d needs %zu bytes of shared memory", block_n, smem);
-  int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  gemm_tc_kernel<EPI, S><<<grid, 64 + 128 * S, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], a, block_n, stages, n_blks, num_tiles);
+  const int num_tiles = ceil_div(m_blks, P) * n_blks;
+  HS_TRY(launch_clustered(gemm_tc_kernel<EPI, S, P>, pair_grid(num_tiles, P), 64 + 128 * S, smem, P, stream, tm[0], tm[1], tm[2],
+                          tm[3], a, block_n, stages, n_blks, num_tiles));
   HS_CHECK_LAUNCH("gemm_tc_kernel");
   return kOk;
 }
 
-template <int EPI>
+template <int EPI, int P>
 int launch_gemm_ares(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int m_blks, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_ares_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_ares_kernel<EPI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
   const int num_kb = ceil_div(a.K, kBlockK);
   const int fixed = num_kb * kATileBytes + 16 * kStageBufBytes + 2048;
   // d(gate) reads its saved pre-activations row-wise through L1: keep ~36 KB of the array as cache
   const int cap = (EPI == kEpiDSwiGLU) ? kSmemMax - 36 * 1024 : kSmemMax;
-  int stages = (cap - fixed) / (block_n * 128);
+  const int b_bytes = block_n / P * 128;
+  int stages = (cap - fixed) / b_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
-  const size_t smem = (size_t)fixed + (size_t)stages * block_n * 128;
+  const size_t smem = (size_t)fixed + (size_t)stages * b_bytes;
   HS_REQUIRE(smem <= (size_t)kSmemMax, "gemm(A-resident): %zu bytes of shared memory", smem);
-  const int grid = m_blks < kNumSMs ? m_blks : kNumSMs;
-  gemm_tc_ares_kernel<EPI><<<grid, 64 + 128 * 4, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], a, block_n, stages, n_blks, m_blks);
+  const int m_units = ceil_div(m_blks, P);
+  HS_TRY(launch_clustered(gemm_tc_ares_kernel<EPI, P>, pair_grid(m_units, P), 64 + 128 * 4, smem, P, stream, tm[0], tm[1], tm[2],
+                          tm[3], a, block_n, stages, n_blks, m_units));
   HS_CHECK_LAUNCH("gemm_tc_ares_kernel");
   return kOk;
 }
@@ -984,14 +1168,29 @@ int launch_gemm_ares(const GemmArgs& a, const CUtensorMap* tm, int block_n, int 
 // wide output + short reduction: keep the A block resident (HSIMAE_GEMM_ARES=0 disables, for A/B measurements)
 bool use_ares(const GemmArgs& a, int epi, int block_n, int n_blks) {
   static const bool enabled = !(getenv("HSIMAE_GEMM_ARES") && atoi(getenv("HSIMAE_GEMM_ARES")) == 0);
-  return enabled && n_blks >= 2 && block_n <= 128 && a.K <= 256 && (epi == kEpiBiasBf16 || epi == kEpiSwiGLU || epi == kEpiDSwiGLU);
+  return enabled && n_blks >= 2 && a.K <= 256 && (epi == kEpiBiasBf16 || epi == kEpiSwiGLU || epi == kEpiDSwiGLU);
+}
+
+// CTA pairs (cta_group::2): each half of the weight tile must be whole 8-row swizzle atoms and a legal share of the
+// MMA's N (HSIMAE_GEMM_PAIR=0 disables, for A/B measurements)
+// Measured (B200, M = 73 728): pairs pay where the operand stream is the limit (long reductions into 256 columns:
+// 53 -> 49 us at K = 1376); the A-resident kernels are bound by their single MMA-issuing thread and their epilogues,
+// which a pair does not relieve (HSIMAE_GEMM_PAIR = 0 | 1 | 2: never | default policy | wherever legal).
+bool use_pair(int block_n, int m_blks, int K, bool ares) {
+  static const int mode = getenv("HSIMAE_GEMM_PAIR") ? atoi(getenv("HSIMAE_GEMM_PAIR")) : 1;
+  if (mode == 0 || block_n % 32 != 0 || m_blks < 2) return false;
+  if (mode >= 2) return true;
+  return !ares && K >= 512;
 }
 
 template <int EPI>
-int launch_gemm(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int num_tiles, cudaStream_t stream) {
+int launch_gemm(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blks, int m_blks, bool ares, bool pair, cudaStream_t stream) {
+  if (ares)
+    return pair ? launch_gemm_ares<EPI, 2>(a, tm, block_n, n_blks, m_blks, stream) : launch_gemm_ares<EPI, 1>(a, tm, block_n, n_blks, m_blks, stream);
   // as many accumulator stages (= epilogue warp groups) as fit in the 512 TMEM columns
-  if (block_n <= 128) return launch_gemm_s<EPI, 4>(a, tm, block_n, n_blks, num_tiles, stream);
-  return launch_gemm_s<EPI, 2>(a, tm, block_n, n_blks, num_tiles, stream);
+  if (block_n <= 128)
+    return pair ? launch_gemm_s<EPI, 4, 2>(a, tm, block_n, n_blks, m_blks, stream) : launch_gemm_s<EPI, 4, 1>(a, tm, block_n, n_blks, m_blks, stream);
+  return pair ? launch_gemm_s<EPI, 2, 2>(a, tm, block_n, n_blks, m_blks, stream) : launch_gemm_s<EPI, 2, 1>(a, tm, block_n, n_blks, m_blks, stream);
 }
 
 int env_int(const char* name, int dflt) {
@@ -1020,8 +1219,13 @@ int pick_block_n(int N, int K, int epi) {
   if (N <= 128) return N;
   // long reductions are MMA/operand-bound: full-width 256-column MMAs, A streamed once
   if (K >= 512 && N % 256 == 0 && (epi == kEpiBiasBf16 || epi == kEpiBiasF32)) return 256;
-  // epilogue-bound kernels: four 128-column accumulator stages (four epilogue warp groups).  Tiles start at
-  // multiples of 128 so the 128-byte output boxes never straddle two tiles; the N tail is clipped by TMA.
+  // short reductions with a wide output run A-resident (use_ares): 256-column MMAs drained as two 128-column halves
+  static const int wide = getenv("HSIMAE_GEMM_ARES_N") ? atoi(getenv("HSIMAE_GEMM_ARES_N")) : 256;
+  static const int wide_gate = getenv("HSIMAE_GEMM_ARES_N_GATE") ? atoi(getenv("HSIMAE_GEMM_ARES_N_GATE")) : 128;
+  if (K <= 256 && N >= 512 && epi == kEpiBiasBf16 && wide == 256) return 256;
+  if (K <= 256 && N >= 512 && (epi == kEpiSwiGLU || epi == kEpiDSwiGLU) && wide_gate == 256) return 256;
+  // otherwise four 128-column accumulator stages (four epilogue warp groups).  Tiles start at multiples of 128 so
+  // the 128-byte output boxes never straddle two tiles; the N tail is clipped by TMA.
   return 128;
 }
 
@@ -1030,37 +1234,35 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   const int block_n = pick_block_n(a.N, a.K, epi);
   const int n_blks = ceil_div(a.N, block_n);
   const int m_blks = ceil_div(a.M, kBlockM);
-  const int num_tiles = n_blks * m_blks;
+  const bool ares = use_ares(a, epi, block_n, n_blks);
+  const bool pair = use_pair(block_n, m_blks, a.K, ares);
   CUtensorMap tm[4];
   HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tm[0]));
-  HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)block_n, &tm[1]));
+  HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(pair ? block_n / 2 : block_n), &tm[1]));
   // output boxes: [32 rows x 128 bytes]
   const uint64_t M = (uint64_t)a.M, N = (uint64_t)a.N;
   switch (epi) {
     case kEpiBiasBf16:
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
       tm[3] = tm[2];
-      if (use_ares(a, epi, block_n, n_blks)) return launch_gemm_ares<kEpiBiasBf16>(a, tm, block_n, n_blks, m_blks, stream);
-      return launch_gemm<kEpiBiasBf16>(a, tm, block_n, n_blks, num_tiles, stream);
+      return launch_gemm<kEpiBiasBf16>(a, tm, block_n, n_blks, m_blks, ares, pair, stream);
     case kEpiBiasF32:
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 32, 32, &tm[2], 4));
       tm[3] = tm[2];
-      return launch_gemm<kEpiBiasF32>(a, tm, block_n, n_blks, num_tiles, stream);
+      return launch_gemm<kEpiBiasF32>(a, tm, block_n, n_blks, m_blks, false, pair, stream);
     case kEpiResidLN:
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 32, 32, &tm[2], 4));
       if (a.gamma) HS_TRY(get_tmap(a.out1, N, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
       else tm[3] = tm[2];
-      return launch_gemm<kEpiResidLN>(a, tm, block_n, n_blks, num_tiles, stream);
+      return launch_gemm<kEpiResidLN>(a, tm, block_n, n_blks, m_blks, false, pair, stream);
     case kEpiSwiGLU:
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
       HS_TRY(get_tmap(a.out1, N / 2, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
-      if (use_ares(a, epi, block_n, n_blks)) return launch_gemm_ares<kEpiSwiGLU>(a, tm, block_n, n_blks, m_blks, stream);
-      return launch_gemm<kEpiSwiGLU>(a, tm, block_n, n_blks, num_tiles, stream);
+      return launch_gemm<kEpiSwiGLU>(a, tm, block_n, n_blks, m_blks, ares, pair, stream);
     case kEpiDSwiGLU:
       HS_TRY(get_tmap(a.out0, 2 * N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
       tm[3] = tm[2];
-      if (use_ares(a, epi, block_n, n_blks)) return launch_gemm_ares<kEpiDSwiGLU>(a, tm, block_n, n_blks, m_blks, stream);
-      return launch_gemm<kEpiDSwiGLU>(a, tm, block_n, n_blks, num_tiles, stream);
+      return launch_gemm<kEpiDSwiGLU>(a, tm, block_n, n_blks, m_blks, ares, pair, stream);
   }
   set_error("gemm: bad epilogue %d", epi);
   return kInvalidArgument;
@@ -1086,26 +1288,27 @@ int launch_colsum(const WgradArgs& a, cudaStream_t stream) {
   return kOk;
 }
 
-int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
-  HS_TRY(wgrad_check_args(a));
+template <int P>
+int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    HS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   // output-column tile: multiple of 64, at most 256
   int kin64 = ceil_div(a.Kin, 64) * 64;
   int tiles_c = ceil_div(kin64, 256);
   int bn = ceil_div(kin64 / 64, tiles_c) * 64;
-  const int tiles_r = ceil_div(a.Nout, kBlockM);
+  if (P == 2 && bn % 128 != 0) bn += 64;       // each CTA of a pair stages whole 64-column boxes
+  const int tiles_r = ceil_div(a.Nout, kBlockM * P);
   const int num_tiles = tiles_r * tiles_c;
   const int kb_total = ceil_div(a.Mred, 64);
-  int splits = kNumSMs / num_tiles;   // one wave: never more CTAs than SMs
+  int splits = kNumSMs / (num_tiles * P);   // one wave: never more CTAs than SMs
   if (splits < 1) splits = 1;
   if (splits > kb_total) splits = kb_total;
   const int kb_per = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, kb_per);
-  const int stage_bytes = (2 + bn / 64) * kBoxBytes;
+  const int stage_bytes = (2 + bn / P / 64) * kBoxBytes;
   int stages = (kSmemBudget - kOnesBytes) / stage_bytes;
   if (stages > 8) stages = 8;
   const size_t smem = (size_t)stages * stage_bytes + kOnesBytes + 1024 + 256;
@@ -1115,18 +1318,30 @@ int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
   // MN-major SWIZZLE_128B canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units:
   // LBO = distance between 64-element atoms along M/N (one TMA box = 8 KB),
   // SBO = distance between groups of 8 reduction rows (1 KB); a K=16 step spans two groups.
-  const uint32_t lbo = (uint32_t)env_int("HSIMAE_WGRAD_LBO", kBoxBytes);
-  const uint32_t sbo = (uint32_t)env_int("HSIMAE_WGRAD_SBO", 1024);
-  const uint32_t kstep = (uint32_t)env_int("HSIMAE_WGRAD_KSTEP", 2048);
+  const uint32_t lbo = kBoxBytes, sbo = 1024, kstep = 2048;
   // bias gradients are fused (ones-operand MMA); HSIMAE_WGRAD_FUSED_BIAS=0 selects the separate column-sum kernel (A/B debugging)
   static const bool fused = env_int("HSIMAE_WGRAD_FUSED_BIAS", 1) != 0;
   WgradArgs k = a;
   if (!fused) { k.bias0 = nullptr; k.bias1 = nullptr; }
-  wgrad_tc_kernel<<<num_tiles * splits, kGemmThreads, smem, stream>>>(tmY, tmX, k, bn, stages, tiles_c, num_tiles, kb_total,
-                                                                      kb_per, lbo, sbo, kstep);
+  HS_TRY(launch_clustered(wgrad_tc_kernel<P>, num_tiles * splits * P, kGemmThreads, smem, P, stream, tmY, tmX, k, bn, stages, tiles_c,
+                          num_tiles, kb_total, kb_per, lbo, sbo, kstep));
   HS_CHECK_LAUNCH("wgrad_tc_kernel");
   if (!fused) return launch_colsum(a, stream);
   return kOk;
 }
 
+int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
+  HS_TRY(wgrad_check_args(a));
+  // CTA pairs halve the L2 reads of X (re-read by every row tile); they need at least two row tiles' worth of rows
+  static const int pair = env_int("HSIMAE_WGRAD_PAIR", 1);
+  if (pair != 0 && a.Nout > 2 * kBlockM) return launch_wgrad<2>(a, stream);
+  return launch_wgrad<1>(a, stream);
+}
+
 }  // namespace hsimae
+
+#ifdef HSIMAE_TRACE
+extern "C" int hsimae_debug_trace(long long* host_out, int n_ll) {
+  return (int)cudaMemcpyFromSymbol(host_out, hsimae::g_trace, (size_t)n_ll * sizeof(long long));
+}
+#endif

@@ -22,3 +22,14 @@ print(os.environ.get("HSIMAE_GEMM_STAGES", "-"),
       "dswiglu %.1f" % t(lambda: ops.gemm(x, w2t, 4, ab=dab)),
       "dgrad1376 %.1f" % t(lambda: ops.gemm(dab, w13t, 0)),
       "dgrad256 %.1f" % t(lambda: ops.gemm(x, wp, 0)))
+
+gw1, gw3 = torch.zeros(684, D, device=dev), torch.zeros(684, D, device=dev)
+gb1, gb3 = torch.zeros(684, device=dev), torch.zeros(684, device=dev)
+gw2, gb2 = torch.zeros(D, 684, device=dev), torch.zeros(D, device=dev)
+dqkv = bf(M, 3 * D); gq, gqb = torch.zeros(3 * D, D, device=dev), torch.zeros(3 * D, device=dev)
+gp, gpb = torch.zeros(D, D, device=dev), torch.zeros(D, device=dev)
+print("wgrad pair=%s -" % os.environ.get("HSIMAE_WGRAD_PAIR", "1"),
+      "dW13 %.1f" % t(lambda: ops.wgrad(dab, x, gw1, dst1=gw3, row_map=1, rows_valid=684, bias0=gb1, bias1=gb3)),
+      "dW2 %.1f" % t(lambda: ops.wgrad(x, g, gw2, cols_valid=684, bias0=gb2)),
+      "dWqkv %.1f" % t(lambda: ops.wgrad(dqkv, x, gq, bias0=gqb)),
+      "dWproj %.1f" % t(lambda: ops.wgrad(x, x, gp, bias0=gpb)))
