@@ -31,6 +31,7 @@ class GemmDesc(C.Structure):
         ("ab", c_void_p), ("ldab", c_i32),
         ("rowscale", c_void_p), ("rs_mode", c_i32), ("rs_K", c_i32), ("rs_len_l", c_i32), ("rs_G", c_i32),
         ("scratch", c_void_p),
+        ("A2", c_void_p), ("lda2", c_i32), ("B2", c_void_p), ("ldb2", c_i32),
     ]
 
 

@@ -58,6 +58,7 @@ struct hsimae_plan {
   std::vector<const void*> last_ptrs;
   const void* last_table;
   bool debug_simt;
+  bool recompute_gate;   // backward recomputes the gated up-projection instead of re-reading saved pre-activations
 };
 
 namespace {
@@ -168,6 +169,8 @@ int build_plan(const hsimae_dims& dm, hsimae_plan* p) {
   p->max_job_elems = 1;
   p->last_table = nullptr;
   p->debug_simt = getenv("HSIMAE_DEBUG_SIMT") && atoi(getenv("HSIMAE_DEBUG_SIMT")) != 0;
+  // HSIMAE_SAVE_GATE=1 keeps the pre-activations (A/B measurements); the CUDA-core checker has no recompute kernel
+  p->recompute_gate = !p->debug_simt && !(getenv("HSIMAE_SAVE_GATE") && atoi(getenv("HSIMAE_SAVE_GATE")) != 0) && p->D <= 256 && p->Dd <= 256;
 
   Builder b{p};
   const int D = p->D, Dd = p->Dd;
@@ -377,7 +380,8 @@ int block_forward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int Hp
   // gated MLP up-projection (Models.py:232)
   a = GemmArgs{};
   a.M = (int)M; a.N = 2 * Hp; a.K = d; a.A = s.ln2; a.lda = d; a.B = c.wb + w.w13; a.ldb = d;
-  a.out0 = s.ab; a.ld0 = 2 * Hp; a.out1 = s.g; a.ld1 = Hp; a.bias = c.wf + w.b13;
+  // the pre-activations are only kept for the checker path; the product path recomputes them in backward
+  a.out0 = c.p->recompute_gate ? nullptr : s.ab; a.ld0 = 2 * Hp; a.out1 = s.g; a.ld1 = Hp; a.bias = c.wf + w.b13;
   HS_TRY(run_gemm(c, a, kEpiSwiGLU));
   // down-projection + residual (+ other branch) + next LayerNorm
   a = GemmArgs{};
@@ -396,8 +400,14 @@ int block_backward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int H
   GemmArgs a{};
   // d(gate): dab = dswiglu(dxb W2, ab)
   a.M = (int)M; a.N = Hp; a.K = d; a.A = b.dxb; a.lda = d; a.B = c.wb + w.w2_t; a.ldb = d;
-  a.out0 = b.dab; a.ld0 = 2 * Hp; a.ab = s.ab; a.ldab = 2 * Hp;
-  HS_TRY(run_gemm(c, a, kEpiDSwiGLU));
+  a.out0 = b.dab; a.ld0 = 2 * Hp;
+  if (c.p->recompute_gate) {
+    a.A2 = s.ln2; a.lda2 = d; a.B2 = c.wb + w.w13; a.ldb2 = d; a.bias = c.wf + w.b13;
+    HS_TRY(run_gemm(c, a, kEpiDGate));
+  } else {
+    a.ab = s.ab; a.ldab = 2 * Hp;
+    HS_TRY(run_gemm(c, a, kEpiDSwiGLU));
+  }
   WgradArgs g{};
   g.Mred = (int)M; g.Nout = d; g.Kin = Hp; g.Y = b.dxb; g.ldy = d; g.X = s.g; g.ldx = Hp;
   g.dst0 = gptr(c, w.w2w); g.ld = H; g.rows_valid = d; g.cols_valid = H; g.bias0 = gptr(c, w.w2b);
@@ -847,6 +857,7 @@ int hsimae_gemm(const hsimae_gemm_desc* d, void* stream) {
   a.M = d->M; a.N = d->N; a.K = d->K; a.A = (const bf16*)d->A; a.lda = d->lda; a.B = (const bf16*)d->B; a.ldb = d->ldb;
   a.out0 = d->out0; a.ld0 = d->ld0; a.out1 = d->out1; a.ld1 = d->ld1; a.bias = d->bias; a.resid = d->resid; a.ldr = d->ldr;
   a.resid2 = d->resid2; a.gamma = d->gamma; a.beta = d->beta; a.stats = d->stats; a.ab = (const bf16*)d->ab; a.ldab = d->ldab;
+  a.A2 = (const bf16*)d->A2; a.lda2 = d->lda2; a.B2 = (const bf16*)d->B2; a.ldb2 = d->ldb2;
   a.rs.scale = d->rowscale; a.rs.mode = d->rs_mode; a.rs.K = d->rs_K > 0 ? d->rs_K : 1; a.rs.len_l = d->rs_len_l > 0 ? d->rs_len_l : 1; a.rs.G = d->rs_G;
   a.ln_eps = 1e-5f;
   if (d->impl == 1) return gemm_simt(a, d->epilogue, d->scratch, (cudaStream_t)stream);

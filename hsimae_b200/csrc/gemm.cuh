@@ -18,7 +18,8 @@ enum Epilogue : int {
   kEpiResidLN = 2,   // out0(f32)  = resid + rs*(acc+bias) [+ resid2];  out1(bf16) = LN(out0); stats
   kEpiSwiGLU = 3,    // out0(bf16, interleaved a|b) = acc + bias;  out1(bf16) = silu(a)*b
   kEpiDSwiGLU = 4,   // acc = dg;  out0(bf16, interleaved) = (dg*b*silu'(a) | dg*silu(a)), a,b from `ab`
-  kNumEpilogues = 5,
+  kEpiDGate = 5,     // like kEpiDSwiGLU, but a|b = A2 * B2^T + bias is RECOMPUTED by a second GEMM in the same kernel
+  kNumEpilogues = 6,
 };
 
 struct GemmArgs {
@@ -35,6 +36,8 @@ struct GemmArgs {
   const float* beta;
   float* stats;                        // [M,2] (mean, rstd) or nullptr
   const __nv_bfloat16* ab; int ldab;   // kEpiDSwiGLU: saved pre-activations (interleaved)
+  const __nv_bfloat16* A2; int lda2;   // kEpiDGate: [M,K] input of the gated projection
+  const __nv_bfloat16* B2; int ldb2;   // kEpiDGate: [2N,K] interleaved w1|w3 (bias = its packed bias)
   float ln_eps;
 };
 

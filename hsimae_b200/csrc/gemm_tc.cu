@@ -45,6 +45,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// One lane of the (converged) warp.  Unlike `lane == 0`, elect.sync tells the compiler that exactly one thread runs the
+// region, so tcgen05 / TMA instructions take their operands straight from uniform registers (no per-instruction
+// "waterfall" loops): the MMA issue loop shrinks from ~80 to ~25 instructions per k-block.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -243,10 +251,11 @@ struct Stager {
   uint32_t base;     // smem address of this warp's two 4 KB buffers (1024-byte aligned)
   int lane;
   bool pending;      // a committed store may still be reading the buffers
+  bool leader = ptx::elect_one();   // the one lane that issues (and later waits for) this warp's bulk stores
   // wait until the TMA unit has finished reading every box this warp handed over
   __device__ __forceinline__ void acquire() {
     if (pending) {
-      if (lane == 0) ptx::bulk_wait_read0();
+      if (leader) ptx::bulk_wait_read0();
       __syncwarp();
       pending = false;
     }
@@ -261,7 +270,7 @@ struct Stager {
   __device__ __forceinline__ void flush(int b, const CUtensorMap* tm, int col, int row) {
     ptx::fence_proxy_async();
     __syncwarp();
-    if (lane == 0) { ptx::tma_store_2d(tm, base + (uint32_t)b * kStageBufBytes, col, row); ptx::bulk_commit(); }
+    if (leader) { ptx::tma_store_2d(tm, base + (uint32_t)b * kStageBufBytes, col, row); ptx::bulk_commit(); }
     pending = true;
   }
 };
@@ -313,7 +322,10 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
     for (; c + 32 <= width; c += 32) tc_bias_chunk<32, F32>(p, acc, st, tmO0, m0, n0, c, width);
     for (; c + 16 <= width; c += 16) tc_bias_chunk<16, F32>(p, acc, st, tmO0, m0, n0, c, width);
   } else if constexpr (EPI == kEpiSwiGLU) {
-    // tile of packed (a|b interleaved by 16) columns; buffer 0: a|b boxes (64 packed columns), buffer 1: the gate box
+    // tile of packed (a|b interleaved by 16) columns; buffer 0: a|b boxes (64 packed columns), buffer 1: the gate box.
+    // The pre-activations are only written when the caller keeps them (out0): the training path recomputes them in
+    // backward (gemm_tc_dgate_kernel) because HBM writes (3.9 TB/s) are the scarce resource of this kernel.
+    const bool keep_ab = p.out0 != nullptr;
     wait_acc();
     for (int c = 0; c + 32 <= width; c += 32) {
       float v[32];
@@ -322,23 +334,27 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
       float g[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a = bf16_round(v[i]), b = bf16_round(v[16 + i]);   // gate on what backward will re-read
+        // gate on what backward will see: the bf16 copy it re-reads, or the fp32 values it recomputes
+        const float a = keep_ab ? bf16_round(v[i]) : v[i], b = keep_ab ? bf16_round(v[16 + i]) : v[16 + i];
         g[i] = a * ptx::sigmoid_fast(a) * b;
       }
-      if ((c & 63) == 0) st.acquire();
-      const int j0 = (c & 63) >> 3;
+      if (keep_ab) {
+        if ((c & 63) == 0) st.acquire();
+        const int j0 = (c & 63) >> 3;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) st.put(0, j0 + i, pack8_bf16(v + 8 * i));
-      if constexpr (G_DIRECT) {
-        // 32 contiguous bytes per thread = one full sector
+        for (int i = 0; i < 4; ++i) st.put(0, j0 + i, pack8_bf16(v + 8 * i));
+      }
+      if (G_DIRECT && keep_ab) {
+        // the single staging box is taken by a|b: 32 contiguous bytes per thread = one full sector
         if (valid) store_bf16_row<16>(reinterpret_cast<__nv_bfloat16*>(p.out1) + (size_t)m * p.ld1 + ((n0 + c) >> 1), g);
       } else {
-        st.put(1, (c >> 5) * 2, pack8_bf16(g));
-        st.put(1, (c >> 5) * 2 + 1, pack8_bf16(g + 8));
+        if (!keep_ab && c == 0) st.acquire();
+        st.put(G_DIRECT ? 0 : 1, (c >> 5) * 2, pack8_bf16(g));
+        st.put(G_DIRECT ? 0 : 1, (c >> 5) * 2 + 1, pack8_bf16(g + 8));
       }
-      if (((c + 32) & 63) == 0 || c + 32 >= width) st.flush(0, tmO0, n0 + (c & ~63), m0);
+      if (keep_ab && (((c + 32) & 63) == 0 || c + 32 >= width)) st.flush(0, tmO0, n0 + (c & ~63), m0);
     }
-    if constexpr (!G_DIRECT) st.flush(1, tmO1, n0 >> 1, m0);
+    if (!(G_DIRECT && keep_ab)) st.flush(G_DIRECT ? 0 : 1, tmO1, n0 >> 1, m0);
   } else if constexpr (EPI == kEpiDSwiGLU) {
     // tile of hidden columns; every 16 of them become 32 packed output columns.  The saved pre-activations of the
     // NEXT chunk are fetched while the current one is being processed (the first fetch overlaps the MMA tail).
@@ -554,7 +570,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       TR_DECL;
       for (int tile = unit0; tile < num_tiles; tile += unit_step) {
@@ -580,7 +596,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       TR_DUMP(0);
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+    if (crank == 0 && ptx::elect_one()) {
       const uint32_t idesc = make_idesc(block_n, false, false, kBlockM * P);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -701,7 +717,7 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       // weight tiles stream continuously (they do not depend on the resident A block)
       int stage = 0; uint32_t phase = 0;
       TR_DECL;
@@ -722,21 +738,20 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       TR_DUMP(0);
     }
   } else if (warp == 1) {
-    // The whole warp walks this loop (uniform control flow keeps counters and descriptors in uniform registers); lane 0
-    // issues.  It owns the resident A block of its CTA: reloaded once every MMA that read the previous block has retired
-    // (a_empty, signalled in both CTAs of a pair); the leader CTA also issues the MMAs.
-    const uint32_t idesc = make_idesc(block_n, false, false, kBlockM * P);
-    const uint32_t a_full_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(a_full), 0) : 0u;
-    const uint64_t adesc0 = make_smem_desc(ptx::smem_u32(a_res), 16, 1024);
-    const uint64_t bdesc0 = make_smem_desc(ptx::smem_u32(ring), 16, 1024);
-    const uint32_t b_units = b_bytes >> 4;
-    int stage = 0; uint32_t phase = 0, aph = 0;
-    int it = 0;
-    TR_DECL;
-    for (int mu = unit0; mu < m_units; mu += unit_step) {
-      const int m0 = (mu * P + crank) * kBlockM;   // may lie past the last row: TMA zero-fills the load and clips the stores
-      if (mu != unit0) ptx::mbar_wait(a_empty, aph ^ 1u);
-      if (lane == 0) {
+    // One elected thread owns the resident A block of its CTA -- reloaded once every MMA that read the previous block has
+    // retired (a_empty, signalled in both CTAs of a pair) -- and, in the leader CTA, issues the MMAs.
+    if (ptx::elect_one()) {
+      const uint32_t idesc = make_idesc(block_n, false, false, kBlockM * P);
+      const uint32_t a_full_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(a_full), 0) : 0u;
+      const uint64_t adesc0 = make_smem_desc(ptx::smem_u32(a_res), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc(ptx::smem_u32(ring), 16, 1024);
+      const uint32_t b_units = b_bytes >> 4;
+      int stage = 0; uint32_t phase = 0, aph = 0;
+      int it = 0;
+      TR_DECL;
+      for (int mu = unit0; mu < m_units; mu += unit_step) {
+        const int m0 = (mu * P + crank) * kBlockM;   // may lie past the last row: TMA zero-fills the load and clips the stores
+        if (mu != unit0) ptx::mbar_wait(a_empty, aph ^ 1u);
         if constexpr (P == 2) {
           if (crank == 0) ptx::mbar_expect_tx(a_full, 2u * a_bytes);
           for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d_pair(a_res + (size_t)kb * kATileBytes, &tmA, a_full_addr, kb * kBlockK, m0);
@@ -744,19 +759,16 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::mbar_expect_tx(a_full, a_bytes);
           for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(a_res + (size_t)kb * kATileBytes, &tmA, a_full, kb * kBlockK, m0);
         }
-      }
-      __syncwarp();
-      if (crank == 0) {
-        TR_WAIT(0, ptx::mbar_wait(a_full, aph));
-        for (int nb = 0; nb < n_blks; ++nb, ++it) {
-          const int as = it % S;
-          TR_WAIT(1, ptx::mbar_wait(tempty + as, ((uint32_t)(it / S) & 1u) ^ 1u));
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_stride;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            TR_WAIT(2, ptx::mbar_wait(full + stage, phase));
+        if (crank == 0) {
+          TR_WAIT(0, ptx::mbar_wait(a_full, aph));
+          for (int nb = 0; nb < n_blks; ++nb, ++it) {
+            const int as = it % S;
+            TR_WAIT(1, ptx::mbar_wait(tempty + as, ((uint32_t)(it / S) & 1u) ^ 1u));
             ptx::tc_fence_after();
-            if (lane == 0) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_stride;
+            for (int kb = 0; kb < num_kb; ++kb) {
+              TR_WAIT(2, ptx::mbar_wait(full + stage, phase));
+              ptx::tc_fence_after();
               const uint64_t adesc = adesc0 + (uint64_t)(kb * (kATileBytes >> 4));
               const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)stage * b_units);
 #pragma unroll
@@ -765,20 +777,16 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 else ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
               }
               if constexpr (P == 2) ptx::umma_commit_pair(empty + stage); else ptx::umma_commit(empty + stage);
-              if (kb == num_kb - 1) {
-                if constexpr (P == 2) ptx::umma_commit_pair(tfull + as); else ptx::umma_commit(tfull + as);
-              }
+              if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
-            __syncwarp();
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            if constexpr (P == 2) ptx::umma_commit_pair(tfull + as); else ptx::umma_commit(tfull + as);
           }
+          if constexpr (P == 2) ptx::umma_commit_pair(a_empty); else ptx::umma_commit(a_empty);
         }
-        if (lane == 0) { if constexpr (P == 2) ptx::umma_commit_pair(a_empty); else ptx::umma_commit(a_empty); }
-        __syncwarp();
+        aph ^= 1u;
       }
-      aph ^= 1u;
+      TR_DUMP(1);
     }
-    if (lane == 0) TR_DUMP(1);
   } else {
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
@@ -800,6 +808,205 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         TR_WAIT(1, tc_epilogue<EPI, 2>(p, acc, st, &tmO0, &tmO1, (mu * P + crank) * kBlockM + q * 32, lane, n0, width, wait_acc));
       } else {
         wait_acc();   // nothing to drain in this half, but the stage is only free once the tile's MMAs have retired
+      }
+      ptx::tc_fence_before();
+      if constexpr (P == 2) ptx::mbar_arrive_cluster(tempty_addr); else ptx::mbar_arrive(tempty + as);
+    }
+    st.acquire();
+    if (warp == 2 && lane == 0) TR_DUMP(2);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (P == 2) ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (P == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// d(gate) with recomputed pre-activations (kEpiDGate): per 64 hidden units one accumulator stage holds
+//   [0,128)   a|b = A2 * B2^T   (the forward's gated up-projection, recomputed: 2 K N2 FLOP per row instead of
+//                                writing 2 N2 bytes per row in forward and reading them back here)
+//   [128,192) dg  = A  * B^T    (gradient w.r.t. the gate output)
+// and the epilogue turns them into the interleaved d(a|b) tile.  Both A blocks stay resident (2 x K/64 tiles of
+// 16 KB); the two weight tiles of a k-block travel in one ring stage.  P = 2: CTA pair, halves of both weight tiles.
+// ---------------------------------------------------------------------------
+constexpr int kGateChunk = 64;
+
+template <int P>
+__global__ void __launch_bounds__(64 + 128 * 2, 1)
+gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                     const __grid_constant__ CUtensorMap tmO0, GemmArgs p, int stages, int n_chunks, int m_units) {
+  constexpr int S = 2;
+  constexpr uint32_t kAccStride = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  constexpr uint32_t kStagingBytes = 8 * kStageBufBytes;   // one box per epilogue warp
+
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const uint32_t a_bytes = (uint32_t)num_kb * kATileBytes;
+  constexpr uint32_t b2_bytes = (uint32_t)(2 * kGateChunk / P) * 128u;   // this CTA's share of the w1|w3 tile
+  constexpr uint32_t b_bytes = (uint32_t)(kGateChunk / P) * 128u;        // ... and of the w2^T tile
+  constexpr uint32_t stage_bytes = b2_bytes + b_bytes;
+  uint8_t* a_res = smem;                 // dy block
+  uint8_t* a2_res = a_res + a_bytes;     // gate-input block
+  uint8_t* ring = a2_res + a_bytes;
+  uint8_t* staging = ring + (size_t)stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint64_t* tempty = tfull + S;
+  uint64_t* a_full = tempty + S;
+  uint64_t* a_empty = a_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = P == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / P, unit_step = (int)gridDim.x / P;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmA2); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmB2); ptx::prefetch_tmap(&tmO0);
+    for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128 * P); }
+    ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (P == 2) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      TR_DECL;
+      for (int mu = unit0; mu < m_units; mu += unit_step)
+        for (int ch = 0; ch < n_chunks; ++ch)
+          for (int kb = 0; kb < num_kb; ++kb) {
+            TR_WAIT(0, ptx::mbar_wait(empty + stage, phase ^ 1u));
+            uint8_t* sb = ring + (size_t)stage * stage_bytes;
+            const int r2 = ch * 2 * kGateChunk + crank * (2 * kGateChunk / P), r1 = ch * kGateChunk + crank * (kGateChunk / P);
+            if constexpr (P == 2) {
+              if (crank == 0) ptx::mbar_expect_tx(full + stage, 2u * stage_bytes);
+              const uint32_t bar = ptx::mapa_rank(ptx::smem_u32(full + stage), 0);
+              ptx::tma_load_2d_pair(sb, &tmB2, bar, kb * kBlockK, r2);
+              ptx::tma_load_2d_pair(sb + b2_bytes, &tmB, bar, kb * kBlockK, r1);
+            } else {
+              ptx::mbar_expect_tx(full + stage, stage_bytes);
+              ptx::tma_load_2d(sb, &tmB2, full + stage, kb * kBlockK, r2);
+              ptx::tma_load_2d(sb + b2_bytes, &tmB, full + stage, kb * kBlockK, r1);
+            }
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+      TR_DUMP(0);
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc_ab = make_idesc(2 * kGateChunk, false, false, kBlockM * P);
+      const uint32_t idesc_dg = make_idesc(kGateChunk, false, false, kBlockM * P);
+      const uint32_t a_full_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(a_full), 0) : 0u;
+      const uint64_t adesc0 = make_smem_desc(ptx::smem_u32(a_res), 16, 1024);
+      const uint64_t a2desc0 = make_smem_desc(ptx::smem_u32(a2_res), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc(ptx::smem_u32(ring), 16, 1024);
+      int stage = 0; uint32_t phase = 0, aph = 0;
+      int it = 0;
+      TR_DECL;
+      for (int mu = unit0; mu < m_units; mu += unit_step) {
+        const int m0 = (mu * P + crank) * kBlockM;
+        if (mu != unit0) ptx::mbar_wait(a_empty, aph ^ 1u);
+        if constexpr (P == 2) {
+          if (crank == 0) ptx::mbar_expect_tx(a_full, 4u * a_bytes);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            ptx::tma_load_2d_pair(a2_res + (size_t)kb * kATileBytes, &tmA2, a_full_addr, kb * kBlockK, m0);
+            ptx::tma_load_2d_pair(a_res + (size_t)kb * kATileBytes, &tmA, a_full_addr, kb * kBlockK, m0);
+          }
+        } else {
+          ptx::mbar_expect_tx(a_full, 2u * a_bytes);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            ptx::tma_load_2d(a2_res + (size_t)kb * kATileBytes, &tmA2, a_full, kb * kBlockK, m0);
+            ptx::tma_load_2d(a_res + (size_t)kb * kATileBytes, &tmA, a_full, kb * kBlockK, m0);
+          }
+        }
+        if (crank == 0) {
+          TR_WAIT(0, ptx::mbar_wait(a_full, aph));
+          for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+            const int as = it % S;
+            TR_WAIT(1, ptx::mbar_wait(tempty + as, ((uint32_t)(it / S) & 1u) ^ 1u));
+            ptx::tc_fence_after();
+            const uint32_t d_ab = tmem_base + (uint32_t)as * kAccStride, d_dg = d_ab + 2 * kGateChunk;
+            for (int kb = 0; kb < num_kb; ++kb) {
+              TR_WAIT(2, ptx::mbar_wait(full + stage, phase));
+              ptx::tc_fence_after();
+              const uint64_t koff = (uint64_t)(kb * (kATileBytes >> 4));
+              const uint64_t b2desc = bdesc0 + (uint64_t)((uint32_t)stage * (stage_bytes >> 4));
+              const uint64_t bdesc = b2desc + (uint64_t)(b2_bytes >> 4);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                if constexpr (P == 2) {
+                  ptx::umma_bf16_pair(d_ab, a2desc0 + koff + (uint64_t)(k * 2), b2desc + (uint64_t)(k * 2), idesc_ab, accum);
+                  ptx::umma_bf16_pair(d_dg, adesc0 + koff + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_dg, accum);
+                } else {
+                  ptx::umma_bf16(d_ab, a2desc0 + koff + (uint64_t)(k * 2), b2desc + (uint64_t)(k * 2), idesc_ab, accum);
+                  ptx::umma_bf16(d_dg, adesc0 + koff + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_dg, accum);
+                }
+              }
+              if constexpr (P == 2) ptx::umma_commit_pair(empty + stage); else ptx::umma_commit(empty + stage);
+              if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+            if constexpr (P == 2) ptx::umma_commit_pair(tfull + as); else ptx::umma_commit(tfull + as);
+          }
+          if constexpr (P == 2) ptx::umma_commit_pair(a_empty); else ptx::umma_commit(a_empty);
+        }
+        aph ^= 1u;
+      }
+      TR_DUMP(1);
+    }
+  } else {
+    const int q = warp & 3;
+    const int as = (warp - 2) >> 2;
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * kStageBufBytes, lane, false};
+    const uint32_t tempty_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(tempty + as), 0) : 0u;
+    const int my_units = unit0 < m_units ? (m_units - 1 - unit0) / unit_step + 1 : 0;
+    const int my_tiles = my_units * n_chunks;
+    const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccStride;
+    TR_DECL;
+    for (int it = as; it < my_tiles; it += S) {
+      const int mu = unit0 + (it / n_chunks) * unit_step, ch = it % n_chunks;
+      const uint32_t aphase = (uint32_t)(it / S) & 1u;
+      const int h0 = ch * kGateChunk;
+      int width = p.N - h0; if (width > kGateChunk) width = kGateChunk;    // hidden units of this chunk (multiple of 16)
+      const int m0 = (mu * P + crank) * kBlockM + q * 32;
+      TR_WAIT(0, ptx::mbar_wait(tfull + as, aphase));
+      ptx::tc_fence_after();
+      for (int c = 0; c < width; c += 16) {
+        float ab[32], dg[16], o[32];
+        ptx::tmem_ld32(acc0 + 2 * c, ab);
+        ptx::tmem_ld16(acc0 + 2 * kGateChunk + c, dg);
+        ptx::tmem_ld_wait();
+        if (p.bias) add_vec<32>(p.bias + 2 * (h0 + c), ab);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = ab[i], b = ab[16 + i];
+          const float sg = ptx::sigmoid_fast(a);
+          o[i] = dg[i] * b * (sg * (1.0f + a * (1.0f - sg)));
+          o[16 + i] = dg[i] * (a * sg);
+        }
+        const int bx = (c & 31) == 0 ? st.begin_box() : 0;
+        const int j0 = ((c & 31) >> 4) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st.put(bx, j0 + i, pack8_bf16(o + 8 * i));
+        if (((c + 16) & 31) == 0 || c + 16 >= width) st.end_box(&tmO0, 2 * (h0 + (c & ~31)), m0);
       }
       ptx::tc_fence_before();
       if constexpr (P == 2) ptx::mbar_arrive_cluster(tempty_addr); else ptx::mbar_arrive(tempty + as);
@@ -883,7 +1090,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         int stage = 0; uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty + stage, phase ^ 1u);
@@ -904,7 +1111,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         }
       }
     } else if (warp == 1) {
-      if (lane == 0 && crank == 0) {
+      if (crank == 0 && ptx::elect_one()) {
         const uint32_t idesc = make_idesc(bn, true, true, kBlockM * P);
         const uint32_t idesc_ones = make_idesc(16, true, true, kBlockM * P);
         const uint64_t ones_desc = make_smem_desc(ptx::smem_u32(ones), lbo, sbo);
@@ -1174,13 +1381,15 @@ bool use_ares(const GemmArgs& a, int epi, int block_n, int n_blks) {
 // CTA pairs (cta_group::2): each half of the weight tile must be whole 8-row swizzle atoms and a legal share of the
 // MMA's N (HSIMAE_GEMM_PAIR=0 disables, for A/B measurements)
 // Measured (B200, M = 73 728): pairs pay where the operand stream is the limit (long reductions into 256 columns:
-// 53 -> 49 us at K = 1376); the A-resident kernels are bound by their single MMA-issuing thread and their epilogues,
-// which a pair does not relieve (HSIMAE_GEMM_PAIR = 0 | 1 | 2: never | default policy | wherever legal).
-bool use_pair(int block_n, int m_blks, int K, bool ares) {
+// 53 -> 49 us at K = 1376), not where the epilogue is (HSIMAE_GEMM_PAIR = 0 | 1 | 2: never | default policy | wherever legal).
+bool use_pair(int block_n, int m_blks, int K, bool ares, bool light_epilogue) {
   static const int mode = getenv("HSIMAE_GEMM_PAIR") ? atoi(getenv("HSIMAE_GEMM_PAIR")) : 1;
   if (mode == 0 || block_n % 32 != 0 || m_blks < 2) return false;
   if (mode >= 2) return true;
-  return !ares && K >= 512;
+  // A-resident kernels stream their weight tiles at the per-SM L2 read rate (~42 B/clk); halving them pays once the
+  // epilogue is light (gated projection that does not keep a|b: 62 -> 58 us), not when it is the limit anyway
+  if (ares) return light_epilogue;
+  return K >= 512;
 }
 
 template <int EPI>
@@ -1191,6 +1400,34 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_blk
   if (block_n <= 128)
     return pair ? launch_gemm_s<EPI, 4, 2>(a, tm, block_n, n_blks, m_blks, stream) : launch_gemm_s<EPI, 4, 1>(a, tm, block_n, n_blks, m_blks, stream);
   return pair ? launch_gemm_s<EPI, 2, 2>(a, tm, block_n, n_blks, m_blks, stream) : launch_gemm_s<EPI, 2, 1>(a, tm, block_n, n_blks, m_blks, stream);
+}
+
+template <int P>
+int launch_gemm_dgate(const GemmArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_dgate_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    configured = true;
+  }
+  const int num_kb = ceil_div(a.K, kBlockK);
+  const int m_blks = ceil_div(a.M, kBlockM);
+  const int fixed = 2 * num_kb * kATileBytes + 8 * kStageBufBytes + 2048;
+  const int stage_bytes = 3 * kGateChunk / P * 128;
+  int stages = (kSmemMax - fixed) / stage_bytes;
+  if (stages > 8) stages = 8;
+  HS_REQUIRE(stages >= 2, "gemm(d-gate): K=%d leaves no room for the weight ring", a.K);
+  const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
+  CUtensorMap tmA, tmA2, tmB, tmB2, tmO;
+  HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tmA));
+  HS_TRY(get_tmap(a.A2, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda2, 64, kBlockM, &tmA2));
+  HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(kGateChunk / P), &tmB));
+  HS_TRY(get_tmap(a.B2, (uint64_t)a.K, (uint64_t)(2 * a.N), (uint64_t)a.ldb2, 64, (uint32_t)(2 * kGateChunk / P), &tmB2));
+  HS_TRY(get_tmap(a.out0, (uint64_t)(2 * a.N), (uint64_t)a.M, (uint64_t)a.ld0, 64, 32, &tmO));
+  const int m_units = ceil_div(m_blks, P);
+  HS_TRY(launch_clustered(gemm_tc_dgate_kernel<P>, pair_grid(m_units, P), 64 + 128 * 2, smem, P, stream, tmA, tmA2, tmB, tmB2, tmO, a,
+                          stages, ceil_div(a.N, kGateChunk), m_units));
+  HS_CHECK_LAUNCH("gemm_tc_dgate_kernel");
+  return kOk;
 }
 
 int env_int(const char* name, int dflt) {
@@ -1210,7 +1447,12 @@ int gemm_check_args(const GemmArgs& a, int epi) {
     HS_REQUIRE(a.resid != nullptr, "gemm: residual epilogue without residual");
   }
   if (epi == kEpiSwiGLU) HS_REQUIRE(a.N % 32 == 0 && a.out1 != nullptr, "gemm: SwiGLU epilogue needs N%%32==0 and out1");
+  if (epi != kEpiSwiGLU) HS_REQUIRE(a.out0 != nullptr, "gemm: missing output");
   if (epi == kEpiDSwiGLU) HS_REQUIRE(a.ab != nullptr, "gemm: dSwiGLU epilogue needs saved pre-activations");
+  if (epi == kEpiDGate) {
+    HS_REQUIRE(a.A2 != nullptr && a.B2 != nullptr && a.out0 != nullptr, "gemm: d-gate epilogue needs the gate input and w1|w3");
+    HS_REQUIRE(a.K <= 256 && a.lda2 % 8 == 0 && a.ldb2 % 8 == 0, "gemm: d-gate epilogue needs K <= 256 (K=%d) and 16-byte aligned rows", a.K);
+  }
   return kOk;
 }
 
@@ -1231,11 +1473,17 @@ int pick_block_n(int N, int K, int epi) {
 
 int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   HS_TRY(gemm_check_args(a, epi));
+  if (epi == kEpiDGate) {
+    static const int pair_mode = getenv("HSIMAE_GEMM_PAIR") ? atoi(getenv("HSIMAE_GEMM_PAIR")) : 1;
+    // pairs halve the weight tiles in shared memory, which is what leaves room for a useful ring next to two A blocks
+    if (pair_mode != 0 && a.M > kBlockM) return launch_gemm_dgate<2>(a, stream);
+    return launch_gemm_dgate<1>(a, stream);
+  }
   const int block_n = pick_block_n(a.N, a.K, epi);
   const int n_blks = ceil_div(a.N, block_n);
   const int m_blks = ceil_div(a.M, kBlockM);
   const bool ares = use_ares(a, epi, block_n, n_blks);
-  const bool pair = use_pair(block_n, m_blks, a.K, ares);
+  const bool pair = use_pair(block_n, m_blks, a.K, ares, epi == kEpiSwiGLU && a.out0 == nullptr);
   CUtensorMap tm[4];
   HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tm[0]));
   HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(pair ? block_n / 2 : block_n), &tm[1]));
@@ -1256,8 +1504,9 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
       else tm[3] = tm[2];
       return launch_gemm<kEpiResidLN>(a, tm, block_n, n_blks, m_blks, false, pair, stream);
     case kEpiSwiGLU:
-      HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
       HS_TRY(get_tmap(a.out1, N / 2, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
+      if (a.out0) HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));
+      else tm[2] = tm[3];
       return launch_gemm<kEpiSwiGLU>(a, tm, block_n, n_blks, m_blks, ares, pair, stream);
     case kEpiDSwiGLU:
       HS_TRY(get_tmap(a.out0, 2 * N, M, (uint64_t)a.ld0, 64, 32, &tm[2]));

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS_BF16, EPI_BIAS_F32, EPI_RESID_LN, EPI_SWIGLU, EPI_DSWIGLU = range(5)
+EPI_BIAS_BF16, EPI_BIAS_F32, EPI_RESID_LN, EPI_SWIGLU, EPI_DSWIGLU, EPI_DGATE = range(6)
 IMPL_TC, IMPL_SIMT = 0, 1
 
 
@@ -28,7 +28,7 @@ def _need_cuda(*ts):
 
 
 def gemm(A, B, epilogue, *, impl=IMPL_TC, bias=None, resid=None, resid2=None, gamma=None, beta=None, ab=None,
-         rowscale=None, rs_mode=0, rs_K=1, rs_len_l=1, rs_G=1, want_stats=True):
+         rowscale=None, rs_mode=0, rs_K=1, rs_len_l=1, rs_G=1, want_stats=True, A2=None, B2=None, keep_ab=True):
     """C = A[M,K] @ B[N,K]^T with the fused epilogue `epilogue`; returns a dict of outputs."""
     _need_cuda(A, B)
     L = _lib.load()
@@ -55,13 +55,19 @@ def gemm(A, B, epilogue, *, impl=IMPL_TC, bias=None, resid=None, resid2=None, ga
                 out["stats"] = torch.empty(M, 2, dtype=torch.float32, device=dev)
                 d.stats = _p(out["stats"])
     elif epilogue == EPI_SWIGLU:
-        out["ab"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        out["ab"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if keep_ab else None
         out["g"] = torch.empty(M, N // 2, dtype=torch.bfloat16, device=dev)
         d.out0, d.ld0, d.out1, d.ld1 = _p(out["ab"]), N, _p(out["g"]), N // 2
     elif epilogue == EPI_DSWIGLU:
         out["dab"] = torch.empty(M, 2 * N, dtype=torch.bfloat16, device=dev)
         d.out0, d.ld0 = _p(out["dab"]), 2 * N
         d.ab, d.ldab = _p(ab), ab.stride(0)
+    elif epilogue == EPI_DGATE:
+        # dab = dswiglu(A @ B^T, A2 @ B2^T + bias): the pre-activations are recomputed inside the kernel
+        _need_cuda(A2, B2)
+        out["dab"] = torch.empty(M, 2 * N, dtype=torch.bfloat16, device=dev)
+        d.out0, d.ld0 = _p(out["dab"]), 2 * N
+        d.A2, d.lda2, d.B2, d.ldb2 = _p(A2), A2.stride(0), _p(B2), B2.stride(0)
     d.bias = _p(bias)
     d.resid, d.ldr, d.resid2 = _p(resid), (resid.stride(0) if resid is not None else 0), _p(resid2)
     d.gamma, d.beta = _p(gamma), _p(beta)

@@ -140,6 +140,8 @@ typedef struct hsimae_gemm_desc {
   const void* ab; int32_t ldab;
   const float* rowscale; int32_t rs_mode, rs_K, rs_len_l, rs_G;
   float* scratch; /* impl 1: fp32 [M,N] */
+  const void* A2; int32_t lda2; /* epilogue 5: bf16 [M,K] input of the gated projection */
+  const void* B2; int32_t ldb2; /* epilogue 5: bf16 [2N,K] interleaved w1|w3; `bias` = its packed bias */
 } hsimae_gemm_desc;
 int hsimae_gemm(const hsimae_gemm_desc* d, void* stream);
 

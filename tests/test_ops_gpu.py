@@ -157,6 +157,41 @@ def test_gemm_swiglu_fwd_bwd(ops, M, d, H):
         assert rel_err(o["dab"][:, cb].float(), b16.grad) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,d,H", [(1000, 256, 684), (300, 64, 172), (129, 128, 344), (4099, 256, 684), (77, 64, 172)])
+def test_gemm_gate_recompute(ops, M, d, H):
+    """Training path: forward keeps only g (gated on the fp32 pre-activations), backward recomputes a|b inside the
+    d(gate) kernel.  Reference: torch fp32 autograd of silu(x W1^T + b1) * (x W3^T + b3) on the same bf16 inputs."""
+    hp = (H + 15) // 16 * 16
+    x = _rand_bf16(M, d, seed=7)
+    w1, w3 = _rand_bf16(H, d, scale=0.08, seed=8), _rand_bf16(H, d, scale=0.08, seed=9)
+    b1, b3 = 0.1 * torch.randn(H, device=DEV), 0.1 * torch.randn(H, device=DEV)
+    W = ops.pack_interleaved(w1, w3, hp)
+    bias = ops.pack_interleaved(b1[:, None], b3[:, None], hp)[:, 0].contiguous()
+    a_ref = (x.float() @ w1.float().t() + b1).requires_grad_(True)
+    b_ref = (x.float() @ w3.float().t() + b3).requires_grad_(True)
+    g_ref = F.silu(a_ref) * b_ref
+    o = ops.gemm(x, W, ops.EPI_SWIGLU, bias=bias, keep_ab=False)
+    assert o["ab"] is None
+    assert rel_err(o["g"][:, :H].float(), g_ref.detach()) < TOL_BF16
+    if hp > H:
+        assert float(o["g"][:, H:].abs().max()) == 0.0
+    dy = _rand_bf16(M, d, scale=0.1, seed=10)
+    w2 = _rand_bf16(d, H, scale=0.08, seed=11)
+    w2t = torch.zeros(hp, d, dtype=torch.bfloat16, device=DEV)
+    w2t[:H] = w2.t()
+    g_ref.backward(dy.float() @ w2.float())
+    idx = torch.arange(H, device=DEV)
+    ca, cb = (idx // 16) * 32 + idx % 16, (idx // 16) * 32 + 16 + idx % 16
+    dab = ops.gemm(dy, w2t, ops.EPI_DGATE, A2=x, B2=W, bias=bias)["dab"]
+    assert rel_err(dab[:, ca].float(), a_ref.grad) < TOL_BF16
+    assert rel_err(dab[:, cb].float(), b_ref.grad) < TOL_BF16
+    if hp > H:   # padded hidden units: zero weights and bias => zero gradient
+        pad = torch.ones(2 * hp, dtype=torch.bool, device=DEV)
+        pad[ca] = False
+        pad[cb] = False
+        assert float(dab[:, pad].float().abs().max()) == 0.0
+
+
 # ---------------------------------------------------------------- wgrad
 @pytest.mark.parametrize("Mred,Nout,Kin", [(5000, 256, 256), (1000, 768, 256), (4097, 64, 64), (3000, 256, 688), (999, 192, 64),
                                            (2000, 64, 176), (63, 128, 128), (1, 64, 64), (8192, 144, 144)])

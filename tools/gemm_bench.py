@@ -20,6 +20,8 @@ print(os.environ.get("HSIMAE_GEMM_STAGES", "-"),
       "w2+ln %.1f" % t(lambda: ops.gemm(g, w2, 2, resid=resid, gamma=gamma, beta=beta)),
       "proj+ln %.1f" % t(lambda: ops.gemm(x, wp, 2, resid=resid, gamma=gamma, beta=beta)),
       "dswiglu %.1f" % t(lambda: ops.gemm(x, w2t, 4, ab=dab)),
+      "swiglu(no ab) %.1f" % t(lambda: ops.gemm(x, w13, 3, keep_ab=False)),
+      "dgate(recompute) %.1f" % t(lambda: ops.gemm(x, w2t, 5, A2=x, B2=w13)),
       "dgrad1376 %.1f" % t(lambda: ops.gemm(dab, w13t, 0)),
       "dgrad256 %.1f" % t(lambda: ops.gemm(x, wp, 0)))
 

@@ -29,3 +29,5 @@ trace("dgrad256 (generic, K=256, N=256)", lambda: ops.gemm(x, wp, 0))
 trace("qkv", lambda: ops.gemm(x, wqkv, 0))
 trace("swiglu", lambda: ops.gemm(x, w13, 3))
 trace("dswiglu", lambda: ops.gemm(x, w2t, 4, ab=dab))
+trace("swiglu (no ab)", lambda: ops.gemm(x, w13, 3, keep_ab=False))
+trace("dgate (recompute): epilogue row = total, tfull-wait", lambda: ops.gemm(x, w2t, 5, A2=x, B2=w13))
