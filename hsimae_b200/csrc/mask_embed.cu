@@ -182,20 +182,23 @@ embed_fwd_kernel(EmbedArgs a) {
 }
 
 // Specialisation for a compile-time patch geometry (the reference's 8x3x3 patches of a 9x9 cube): the (u,p,q)
-// loops unroll into immediate shared-memory offsets, so the inner loop is one broadcast LDS + one FFMA per MAC.
-// Two samples are in flight per CTA (one per 256-thread half) sharing the transposed weight tile in smem: twice
-// the warps per SM to cover the broadcast-LDS -> FFMA latency.
-constexpr int kEmbedSlots = 2;
+// loops unroll into immediate shared-memory offsets.  The kernel is bound by shared-memory loads, not FMAs, so every
+// thread owns kEmbedCh output channels and TK tokens: one broadcast LDS of a cube value feeds kEmbedCh FMAs and one
+// LDS of a weight feeds TK.  kEmbedSlots samples are in flight per CTA (64 threads each) sharing the transposed
+// weight tile in shared memory.
+constexpr int kEmbedSlots = 4;
+constexpr int kSlotThreads = 64;
+constexpr int kEmbedCh = 4;     // output channels per thread: each staged cube value feeds kEmbedCh FMAs
 
 template <int U, int P, int IMG, int TK>
-__global__ void __launch_bounds__(kEmbedThreads * kEmbedSlots)
+__global__ void __launch_bounds__(kSlotThreads * kEmbedSlots)
 embed_fwd_fixed_kernel(EmbedArgs a) {
   extern __shared__ float sm[];
   const PatchGeom g = a.g;
   constexpr int PK = U * P * P;
   const int D = a.D, K = a.K;
-  const int slot = threadIdx.x / kEmbedThreads, tid = threadIdx.x % kEmbedThreads;
-  float* sW = sm;                                              // [PK][D] shared by both slots
+  const int slot = threadIdx.x / kSlotThreads, tid = threadIdx.x % kSlotThreads;
+  float* sW = sm;                                              // [PK][D] shared by all slots
   const size_t slot_floats = ((size_t)g.cube + (size_t)K * D + 2 * (size_t)K + 3) / 4 * 4;   // keep every slot 16-byte aligned
   float* sCube = sW + (size_t)PK * D + slot * slot_floats;     // [cube]
   float* sX = sCube + g.cube;                                  // [K][D]
@@ -205,15 +208,16 @@ embed_fwd_fixed_kernel(EmbedArgs a) {
     const int d = i / PK, j = i - d * PK;
     sW[(size_t)j * D + d] = a.W[i];
   }
-  const int warp = tid >> 5, lane = tid & 31, nwarps = kEmbedThreads >> 5;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = kSlotThreads >> 5;
+  const int dq = D / kEmbedCh;                                 // thread t owns channels t, t + dq, t + 2 dq, t + 3 dq
   const int rounds = (a.N + gridDim.x * kEmbedSlots - 1) / (gridDim.x * kEmbedSlots);
   for (int rd = 0; rd < rounds; ++rd) {
     const int n = (rd * gridDim.x + blockIdx.x) * kEmbedSlots + slot;
     const bool live = n < a.N;
     __syncthreads();
     if (live) {
-      stage_cube(a, g, n, sCube, tid, kEmbedThreads);
-      for (int i = tid; i < K; i += kEmbedThreads) {
+      stage_cube(a, g, n, sCube, tid, kSlotThreads);
+      for (int i = tid; i < K; i += kSlotThreads) {
         const int tok = a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i;
         sTok[i] = tok;
         sBase[i] = cube_index(g, tok, 0);
@@ -221,26 +225,42 @@ embed_fwd_fixed_kernel(EmbedArgs a) {
     }
     __syncthreads();
     if (live) {
-      for (int d = tid; d < D; d += kEmbedThreads) {
-        const float b = a.bias ? a.bias[d] : 0.f;
+      for (int d = tid; d < dq; d += kSlotThreads) {
+        float b[kEmbedCh];
+#pragma unroll
+        for (int c = 0; c < kEmbedCh; ++c) b[c] = a.bias ? a.bias[d + c * dq] : 0.f;
         for (int k0 = 0; k0 < K; k0 += TK) {
-          float acc[TK];
+          float acc[TK][kEmbedCh];
           const float* base[TK];
 #pragma unroll
-          for (int k = 0; k < TK; ++k) { acc[k] = 0.f; base[k] = sCube + sBase[k0 + k < K ? k0 + k : K - 1]; }
+          for (int k = 0; k < TK; ++k) {
+            base[k] = sCube + sBase[k0 + k < K ? k0 + k : K - 1];
+#pragma unroll
+            for (int c = 0; c < kEmbedCh; ++c) acc[k][c] = 0.f;
+          }
 #pragma unroll
           for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int pp = 0; pp < P; ++pp)
 #pragma unroll
               for (int q = 0; q < P; ++q) {
-                const float w = sW[(size_t)((u * P + pp) * P + q) * D + d];
+                float w[kEmbedCh];
 #pragma unroll
-                for (int k = 0; k < TK; ++k) acc[k] = fmaf(base[k][(u * IMG + pp) * IMG + q], w, acc[k]);
+                for (int c = 0; c < kEmbedCh; ++c) w[c] = sW[(size_t)((u * P + pp) * P + q) * D + d + c * dq];
+#pragma unroll
+                for (int k = 0; k < TK; ++k) {
+                  const float v = base[k][(u * IMG + pp) * IMG + q];
+#pragma unroll
+                  for (int c = 0; c < kEmbedCh; ++c) acc[k][c] = fmaf(v, w[c], acc[k][c]);
+                }
               }
 #pragma unroll
           for (int k = 0; k < TK; ++k)
-            if (k0 + k < K) sX[(size_t)(k0 + k) * D + d] = acc[k] + b + __ldg(a.pos + (size_t)sTok[k0 + k] * D + d);
+            if (k0 + k < K) {
+#pragma unroll
+              for (int c = 0; c < kEmbedCh; ++c)
+                sX[(size_t)(k0 + k) * D + d + c * dq] = acc[k][c] + b[c] + __ldg(a.pos + (size_t)sTok[k0 + k] * D + d + c * dq);
+            }
         }
       }
     }
@@ -285,10 +305,10 @@ int launch_embed_fwd(const EmbedArgs& a, cudaStream_t stream) {
   HS_REQUIRE(smem <= 227 * 1024, "embed: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
   const int grid = a.N < kNumSMs ? a.N : kNumSMs;
   const size_t smem2 = ((size_t)a.g.PK * a.D + kEmbedSlots * (((size_t)a.g.cube + (size_t)a.K * a.D + 2 * (size_t)a.K + 3) / 4 * 4)) * sizeof(float);
-  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9 && smem2 <= 227 * 1024) {
+  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9 && smem2 <= 227 * 1024 && a.D % kEmbedCh == 0) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_fixed_kernel<8, 3, 9, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int grid2 = ceil_div(a.N, kEmbedSlots) < kNumSMs ? ceil_div(a.N, kEmbedSlots) : kNumSMs;
-    embed_fwd_fixed_kernel<8, 3, 9, 9><<<grid2, kEmbedThreads * kEmbedSlots, smem2, stream>>>(a);
+    embed_fwd_fixed_kernel<8, 3, 9, 9><<<grid2, kSlotThreads * kEmbedSlots, smem2, stream>>>(a);
   } else {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     embed_fwd_kernel<<<grid, kEmbedThreads, smem, stream>>>(a);
@@ -353,47 +373,67 @@ embed_bwd_kernel(EmbedBwdArgs a) {
   }
 }
 
+// Each thread owns kBwdCh output channels (d, d + D/kBwdCh, ...) and their PK accumulators: one broadcast LDS of a
+// cube value feeds kBwdCh FMAs (the loop is bound by shared-memory loads).
+constexpr int kBwdCh = 2;
+
 template <int U, int P, int IMG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 embed_bwd_fixed_kernel(EmbedBwdArgs a) {
   extern __shared__ float sm[];
   const PatchGeom g = a.g;
   constexpr int PK = U * P * P;
   const int D = a.D, K = a.K;
+  const int dq = D / kBwdCh;
   float* sCube = sm;
   int* sBase = reinterpret_cast<int*>(sCube + g.cube);
-  for (int d0 = 0; d0 < D; d0 += blockDim.x) {
+  for (int d0 = 0; d0 < dq; d0 += blockDim.x) {
     const int d = d0 + threadIdx.x;
-    float acc[PK];
+    float acc[kBwdCh][PK];
+    float bsum[kBwdCh];
 #pragma unroll
-    for (int j = 0; j < PK; ++j) acc[j] = 0.f;
-    float bsum = 0.f;
+    for (int c = 0; c < kBwdCh; ++c) {
+      bsum[c] = 0.f;
+#pragma unroll
+      for (int j = 0; j < PK; ++j) acc[c][j] = 0.f;
+    }
     for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
       __syncthreads();
       const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
       for (int i = threadIdx.x; i < g.cube / 4; i += blockDim.x) reinterpret_cast<float4*>(sCube)[i] = ld_stream_f4(src + i);
       for (int i = threadIdx.x; i < K; i += blockDim.x) sBase[i] = cube_index(g, a.ids_keep ? a.ids_keep[(size_t)n * K + i] : i, 0);
       __syncthreads();
-      if (d < D) {
+      if (d < dq) {
         for (int k = 0; k < K; ++k) {
           const size_t m = (size_t)n * K + k;
-          float gv = a.dx_a[m * D + d];
-          if (a.dx_b) gv += a.dx_b[m * D + d];
-          bsum += gv;
+          float gv[kBwdCh];
+#pragma unroll
+          for (int c = 0; c < kBwdCh; ++c) {
+            gv[c] = a.dx_a[m * D + d + c * dq];
+            if (a.dx_b) gv[c] += a.dx_b[m * D + d + c * dq];
+            bsum[c] += gv[c];
+          }
           const float* base = sCube + sBase[k];
 #pragma unroll
           for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int pp = 0; pp < P; ++pp)
 #pragma unroll
-              for (int q = 0; q < P; ++q) acc[(u * P + pp) * P + q] = fmaf(gv, base[(u * IMG + pp) * IMG + q], acc[(u * P + pp) * P + q]);
+              for (int q = 0; q < P; ++q) {
+                const float v = base[(u * IMG + pp) * IMG + q];
+#pragma unroll
+                for (int c = 0; c < kBwdCh; ++c) acc[c][(u * P + pp) * P + q] = fmaf(gv[c], v, acc[c][(u * P + pp) * P + q]);
+              }
         }
       }
     }
-    if (d < D) {
+    if (d < dq) {
 #pragma unroll
-      for (int j = 0; j < PK; ++j) atomicAdd(a.dW + (size_t)d * PK + j, acc[j]);
-      if (a.dbias) atomicAdd(a.dbias + d, bsum);
+      for (int c = 0; c < kBwdCh; ++c) {
+#pragma unroll
+        for (int j = 0; j < PK; ++j) atomicAdd(a.dW + (size_t)(d + c * dq) * PK + j, acc[c][j]);
+        if (a.dbias) atomicAdd(a.dbias + d + c * dq, bsum[c]);
+      }
     }
   }
 }
@@ -404,9 +444,10 @@ int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream) {
   const size_t smem = (size_t)a.g.cube * sizeof(float) + ((size_t)a.K * a.g.PK + a.K) * sizeof(int);
   HS_REQUIRE(smem <= 227 * 1024, "embed_bwd: needs %zu bytes of shared memory", smem);
   const int grid = a.N < 2 * kNumSMs ? a.N : 2 * kNumSMs;   // two CTAs per SM
-  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9) {
+  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9 && a.D % kBwdCh == 0) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_fixed_kernel<8, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    embed_bwd_fixed_kernel<8, 3, 9><<<grid, 256, smem, stream>>>(a);
+    const int grid4 = a.N < 4 * kNumSMs ? a.N : 4 * kNumSMs;   // 128-thread CTAs, four per SM
+    embed_bwd_fixed_kernel<8, 3, 9><<<grid4, 128, smem, stream>>>(a);
   } else if (a.g.PK <= 72) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     embed_bwd_kernel<72><<<grid, 256, smem, stream>>>(a);
