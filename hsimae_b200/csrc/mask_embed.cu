@@ -269,18 +269,37 @@ embed_fwd_fixed_kernel(EmbedArgs a) {
       for (int k = warp; k < K; k += nwarps) {
         const float* xr = sX + (size_t)k * D;
         const size_t m = (size_t)n * K + k;
+        // lane l owns channels [8 l, 8 l + 8) of every 256-channel slab: 128-bit shared loads and global stores
         float s = 0.f;
-        for (int i = lane; i < D; i += 32) s += xr[i];
+        for (int i = lane * 8; i < D; i += 256) {
+          const float4 v0 = *reinterpret_cast<const float4*>(xr + i), v1 = *reinterpret_cast<const float4*>(xr + i + 4);
+          s += (v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w);
+        }
         const float mean = warp_sum(s) / D;
         float sq = 0.f;
-        for (int i = lane; i < D; i += 32) { const float dv = xr[i] - mean; sq = fmaf(dv, dv, sq); }
+        for (int i = lane * 8; i < D; i += 256) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float dv = xr[i + j] - mean; sq = fmaf(dv, dv, sq); }
+        }
         const float rstd = rsqrtf(warp_sum(sq) / D + a.eps);
-        for (int i = lane; i < D; i += 32) {
-          const float v = xr[i];
-          a.x[m * D + i] = v;
-          const float xh = (v - mean) * rstd;
-          if (a.ln_a) a.ln_a[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_a[i], a.beta_a[i]));
-          if (a.ln_b) a.ln_b[m * D + i] = __float2bfloat16_rn(fmaf(xh, a.gamma_b[i], a.beta_b[i]));
+        for (int i = lane * 8; i < D; i += 256) {
+          float v[8], xh[8], o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] = xr[i + j]; xh[j] = (v[j] - mean) * rstd; }
+          *reinterpret_cast<float4*>(a.x + m * D + i) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(a.x + m * D + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          if (a.ln_a) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[j], __ldg(a.gamma_a + i + j), __ldg(a.beta_a + i + j));
+            *reinterpret_cast<uint4*>(a.ln_a + m * D + i) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          }
+          if (a.ln_b) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[j], __ldg(a.gamma_b + i + j), __ldg(a.beta_b + i + j));
+            *reinterpret_cast<uint4*>(a.ln_b + m * D + i) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          }
         }
         if (lane == 0) {
           if (a.stats_a) { a.stats_a[2 * m] = mean; a.stats_a[2 * m + 1] = rstd; }
@@ -305,7 +324,7 @@ int launch_embed_fwd(const EmbedArgs& a, cudaStream_t stream) {
   HS_REQUIRE(smem <= 227 * 1024, "embed: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
   const int grid = a.N < kNumSMs ? a.N : kNumSMs;
   const size_t smem2 = ((size_t)a.g.PK * a.D + kEmbedSlots * (((size_t)a.g.cube + (size_t)a.K * a.D + 2 * (size_t)a.K + 3) / 4 * 4)) * sizeof(float);
-  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9 && smem2 <= 227 * 1024 && a.D % kEmbedCh == 0) {
+  if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9 && smem2 <= 227 * 1024 && a.D % 8 == 0) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_fwd_fixed_kernel<8, 3, 9, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int grid2 = ceil_div(a.N, kEmbedSlots) < kNumSMs ? ceil_div(a.N, kEmbedSlots) : kNumSMs;
     embed_fwd_fixed_kernel<8, 3, 9, 9><<<grid2, kSlotThreads * kEmbedSlots, smem2, stream>>>(a);
@@ -430,8 +449,10 @@ embed_bwd_fixed_kernel(EmbedBwdArgs a) {
     if (d < dq) {
 #pragma unroll
       for (int c = 0; c < kBwdCh; ++c) {
+        // PK is a multiple of 4 and every row of dW starts 16-byte aligned: one vector reduction per 4 accumulators
 #pragma unroll
-        for (int j = 0; j < PK; ++j) atomicAdd(a.dW + (size_t)(d + c * dq) * PK + j, acc[c][j]);
+        for (int j = 0; j < PK; j += 4)
+          red_add_f32x4(a.dW + (size_t)(d + c * dq) * PK + j, acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]);
         if (a.dbias) atomicAdd(a.dbias + d + c * dq, bsum[c]);
       }
     }
@@ -446,8 +467,8 @@ int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream) {
   const int grid = a.N < 2 * kNumSMs ? a.N : 2 * kNumSMs;   // two CTAs per SM
   if (a.g.u == 8 && a.g.p == 3 && a.g.img == 9 && a.D % kBwdCh == 0) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_fixed_kernel<8, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid4 = a.N < 4 * kNumSMs ? a.N : 4 * kNumSMs;   // 128-thread CTAs, four per SM
-    embed_bwd_fixed_kernel<8, 3, 9><<<grid4, 128, smem, stream>>>(a);
+    // every CTA flushes a full [D, PK] partial with reductions: as few CTAs as keep the SMs busy
+    embed_bwd_fixed_kernel<8, 3, 9><<<grid, 128, smem, stream>>>(a);
   } else if (a.g.PK <= 72) {
     HS_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     embed_bwd_kernel<72><<<grid, 256, smem, stream>>>(a);
