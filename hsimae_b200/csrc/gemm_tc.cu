@@ -838,7 +838,7 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 constexpr int kGateChunk = 64;
 
 template <int P>
-__global__ void __launch_bounds__(64 + 128 * 2, 1)
+__global__ void __launch_bounds__(64 + 128 * 4, 1)
 gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                      const __grid_constant__ CUtensorMap tmO0, GemmArgs p, int stages, int n_chunks, int m_units) {
@@ -847,7 +847,8 @@ gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  constexpr uint32_t kStagingBytes = 8 * kStageBufBytes;   // one box per epilogue warp
+  constexpr uint32_t kHalfBoxBytes = 32 * 64;              // [32 rows x 64 bytes], 64B swizzle: 16 hidden units of d(a|b)
+  constexpr uint32_t kStagingBytes = 16 * kHalfBoxBytes;   // one half box per epilogue warp
 
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
   const uint32_t a_bytes = (uint32_t)num_kb * kATileBytes;
@@ -874,7 +875,7 @@ gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmA2); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmB2); ptx::prefetch_tmap(&tmO0);
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128 * P); }
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 256 * P); }
     ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
     ptx::fence_barrier_init();
   }
@@ -975,9 +976,14 @@ gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       TR_DUMP(1);
     }
   } else {
+    // Four epilogue groups: stage = group / 2, and each group drains one 32-unit half of the 64 hidden units, so
+    // every accumulator stage is emptied by 8 warps (the epilogue, not the MMA, is the longer side of this kernel).
     const int q = warp & 3;
-    const int as = (warp - 2) >> 2;
-    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * kStageBufBytes, lane, false};
+    const int grp = (warp - 2) >> 2;
+    const int as = grp >> 1, half = grp & 1;
+    const uint32_t box = ptx::smem_u32(staging) + (uint32_t)(warp - 2) * kHalfBoxBytes;
+    const bool leader = ptx::elect_one();
+    bool pending = false;
     const uint32_t tempty_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(tempty + as), 0) : 0u;
     const int my_units = unit0 < m_units ? (m_units - 1 - unit0) / unit_step + 1 : 0;
     const int my_tiles = my_units * n_chunks;
@@ -986,15 +992,16 @@ gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int it = as; it < my_tiles; it += S) {
       const int mu = unit0 + (it / n_chunks) * unit_step, ch = it % n_chunks;
       const uint32_t aphase = (uint32_t)(it / S) & 1u;
-      const int h0 = ch * kGateChunk;
-      int width = p.N - h0; if (width > kGateChunk) width = kGateChunk;    // hidden units of this chunk (multiple of 16)
+      const int h0 = ch * kGateChunk + half * (kGateChunk / 2);
+      int width = p.N - h0; if (width > kGateChunk / 2) width = kGateChunk / 2;   // hidden units of this half (multiple of 16, may be <= 0)
       const int m0 = (mu * P + crank) * kBlockM + q * 32;
       TR_WAIT(0, ptx::mbar_wait(tfull + as, aphase));
       ptx::tc_fence_after();
       for (int c = 0; c < width; c += 16) {
+        const int cc = half * (kGateChunk / 2) + c;      // hidden offset inside the chunk
         float ab[32], dg[16], o[32];
-        ptx::tmem_ld32(acc0 + 2 * c, ab);
-        ptx::tmem_ld16(acc0 + 2 * kGateChunk + c, dg);
+        ptx::tmem_ld32(acc0 + 2 * cc, ab);
+        ptx::tmem_ld16(acc0 + 2 * kGateChunk + cc, dg);
         ptx::tmem_ld_wait();
         if (p.bias) add_vec<32>(p.bias + 2 * (h0 + c), ab);
 #pragma unroll
@@ -1004,16 +1011,20 @@ gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           o[i] = dg[i] * b * (sg * (1.0f + a * (1.0f - sg)));
           o[16 + i] = dg[i] * (a * sg);
         }
-        const int bx = (c & 31) == 0 ? st.begin_box() : 0;
-        const int j0 = ((c & 31) >> 4) * 4;
+        if (pending) { if (leader) ptx::bulk_wait_read0(); __syncwarp(); pending = false; }
+        // 64-byte row of the half box; 64B swizzle: 16-byte piece index XOR ((row >> 1) & 3)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) st.put(bx, j0 + i, pack8_bf16(o + 8 * i));
-        if (((c + 16) & 31) == 0 || c + 16 >= width) st.end_box(&tmO0, 2 * (h0 + (c & ~31)), m0);
+        for (int i = 0; i < 4; ++i)
+          ptx::st_shared_v4(box + (uint32_t)lane * 64u + (uint32_t)((i ^ ((lane >> 1) & 3)) << 4), pack8_bf16(o + 8 * i));
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (leader) { ptx::tma_store_2d(&tmO0, box, 2 * (h0 + c), m0); ptx::bulk_commit(); }
+        pending = true;
       }
       ptx::tc_fence_before();
       if constexpr (P == 2) ptx::mbar_arrive_cluster(tempty_addr); else ptx::mbar_arrive(tempty + as);
     }
-    st.acquire();
+    if (pending) { if (leader) ptx::bulk_wait_read0(); __syncwarp(); }
     if (warp == 2 && lane == 0) TR_DUMP(2);
   }
 
@@ -1266,7 +1277,7 @@ std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // 2-D tensor of bf16 (esz 2) or fp32 (esz 4), dim0 contiguous (d0 elements), d1 rows of `pitch` elements,
-// box {b0, b1} with b0 * esz == 128 bytes, 128B swizzle.
+// box {b0, b1} with b0 * esz == 128 bytes (128B swizzle) or 64 bytes (64B swizzle).
 int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t b0, uint32_t b1, CUtensorMap* out, uint32_t esz = 2) {
   MapKey key{ptr, d0, d1, pitch, b0, b1, esz};
   {
@@ -1278,14 +1289,15 @@ int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t pitch, uint32_t
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return kCudaError; }
   HS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand %p is not 16-byte aligned", ptr);
   HS_REQUIRE((pitch * esz) % 16 == 0, "TMA operand pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)pitch);
-  HS_REQUIRE(b0 * esz == 128 && b1 <= 256, "bad TMA box {%u,%u}", b0, b1);
+  HS_REQUIRE((b0 * esz == 128 || b0 * esz == 64) && b1 <= 256, "bad TMA box {%u,%u}", b0, b1);
   cuuint64_t dims[2] = {d0, d1};
   cuuint64_t strides[1] = {pitch * esz};
   cuuint32_t box[2] = {b0, b1};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, b0 * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p dims={%llu,%llu} pitch=%llu box={%u,%u}", (int)r, ptr,
@@ -1413,7 +1425,7 @@ int launch_gemm_dgate(const GemmArgs& a, cudaStream_t stream) {
   }
   const int num_kb = ceil_div(a.K, kBlockK);
   const int m_blks = ceil_div(a.M, kBlockM);
-  const int fixed = 2 * num_kb * kATileBytes + 8 * kStageBufBytes + 2048;
+  const int fixed = 2 * num_kb * kATileBytes + 16 * 32 * 64 + 2048;
   const int stage_bytes = 3 * kGateChunk / P * 128;
   int stages = (kSmemMax - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -1424,9 +1436,9 @@ int launch_gemm_dgate(const GemmArgs& a, cudaStream_t stream) {
   HS_TRY(get_tmap(a.A2, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda2, 64, kBlockM, &tmA2));
   HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(kGateChunk / P), &tmB));
   HS_TRY(get_tmap(a.B2, (uint64_t)a.K, (uint64_t)(2 * a.N), (uint64_t)a.ldb2, 64, (uint32_t)(2 * kGateChunk / P), &tmB2));
-  HS_TRY(get_tmap(a.out0, (uint64_t)(2 * a.N), (uint64_t)a.M, (uint64_t)a.ld0, 64, 32, &tmO));
+  HS_TRY(get_tmap(a.out0, (uint64_t)(2 * a.N), (uint64_t)a.M, (uint64_t)a.ld0, 32, 32, &tmO));   // half boxes: 32 packed columns
   const int m_units = ceil_div(m_blks, P);
-  HS_TRY(launch_clustered(gemm_tc_dgate_kernel<P>, pair_grid(m_units, P), 64 + 128 * 2, smem, P, stream, tmA, tmA2, tmB, tmB2, tmO, a,
+  HS_TRY(launch_clustered(gemm_tc_dgate_kernel<P>, pair_grid(m_units, P), 64 + 128 * 4, smem, P, stream, tmA, tmA2, tmB, tmB2, tmO, a,
                           stages, ceil_div(a.N, kGateChunk), m_units));
   HS_CHECK_LAUNCH("gemm_tc_dgate_kernel");
   return kOk;
