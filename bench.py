@@ -145,17 +145,17 @@ def time_events(fn, iters: int):
 
 def ncu_traffic(cand: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the candidate kernel, from the committed
-    `ncu --set full` capture (profiles/r01b_ncu_full_kernels.json; same shapes as timed here), or None"""
-    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_kernels.json")
-    want = {"gemm_tc_kernel<SwiGLU>": ("gemm_tc_kernel<3", 0), "gemm_tc_kernel<ResidLN>": ("gemm_tc_kernel<2", 0),
-            "gemm_tc_kernel<Bias> qkv": ("gemm_tc_kernel<0, 4", 0), "wgrad_tc_kernel dW13": ("wgrad_tc_kernel", 0),
-            "gemm_tc_kernel<Bias> dgrad": ("gemm_tc_kernel<0, 2", 0)}
+    `ncu --set full` capture (profiles/r01c_ncu_full_kernels.json, written by tools/ncu_summary.py from a
+    tools/prof_kernels.py run at the shapes timed here), or None"""
+    path = os.path.join(ROOT, "profiles", "r01c_ncu_full_kernels.json")
+    want = {"gemm_tc_dgate_kernel": "d(gate)", "gemm_tc_ares_kernel<SwiGLU": "gated up-projection", "gemm_tc_kernel<ResidLN>": "down-projection",
+            "gemm_tc_ares_kernel<Bias> qkv": "qkv projection", "wgrad_tc_kernel dW13": "wgrad dW13", "gemm_tc_kernel<Bias> dgrad": "dgrad K=1376"}
     try:
         rows = json.load(open(path))
-        for key, (prefix, nth) in want.items():
+        for key, label in want.items():
             if cand.startswith(key):
-                hits = [r for r in rows if prefix in r["kernel"]]
-                return (hits[nth]["dram_read_mb"] + hits[nth]["dram_write_mb"]) * 1e6
+                hit = [r for r in rows if r["label"].startswith(label)][0]
+                return hit["dram_read_bytes"] + hit["dram_write_bytes"]
     except Exception:
         pass
     return None
@@ -163,24 +163,28 @@ def ncu_traffic(cand: str):
 
 def dominant_kernel_roofline(batch: int, pk):
     """Times the per-block GEMM kernels at the bench shapes (M = batch*18 encoder token rows) in isolation, picks the
-    class with the largest share of a step, and reports it against its binding roofline."""
+    class with the largest share of a step, and reports it against its binding roofline.  Algorithmic work per launch
+    (DESIGN.md section 3): FLOPs = 2 M N K per contraction; bytes = every operand / result tensor once."""
     from hsimae_b200 import ops
     dev = "cuda"
     M, D, H = batch * 18, 256, 688
     bf = lambda *s: torch.randn(*s, device=dev).to(torch.bfloat16)
-    x, w13, wqkv, w2, wp = bf(M, D), bf(2 * H, D) * 0.05, bf(3 * D, D) * 0.05, bf(D, H) * 0.05, bf(D, D) * 0.05
+    x, w13, wqkv, w2 = bf(M, D), bf(2 * H, D) * 0.05, bf(3 * D, D) * 0.05, bf(D, H) * 0.05
+    w2t = bf(H, D) * 0.05
     g, resid = bf(M, H), torch.randn(M, D, device=dev)
     gamma, beta = torch.ones(D, device=dev), torch.zeros(D, device=dev)
-    dab, dqkv = bf(M, 2 * H), bf(M, 3 * D)
+    dab = bf(M, 2 * H)
     gw13 = torch.zeros(684, D, device=dev); gw13b = torch.zeros(684, D, device=dev)
     per_step = 21   # encoder blocks per direction
     cands = {
-        "gemm_tc_kernel<SwiGLU> [M,256]x[256,1376]": (lambda: ops.gemm(x, w13, ops.EPI_SWIGLU), 2 * M * 2 * H * D,
-                                                      2 * (M * D + 2 * H * D + M * 2 * H + M * H), per_step),
+        "gemm_tc_dgate_kernel d(a|b) from [M,256]x{[256,1376],[256,688]}": (
+            lambda: ops.gemm(x, w2t, ops.EPI_DGATE, A2=x, B2=w13), 2 * M * D * 3 * H, 2 * (2 * M * D + 3 * H * D + M * 2 * H), per_step),
+        "gemm_tc_ares_kernel<SwiGLU, g only> [M,256]x[256,1376]": (
+            lambda: ops.gemm(x, w13, ops.EPI_SWIGLU, keep_ab=False), 2 * M * 2 * H * D, 2 * (M * D + 2 * H * D + M * H), per_step),
         "gemm_tc_kernel<ResidLN> [M,688]x[688,256]": (lambda: ops.gemm(g, w2, ops.EPI_RESID_LN, resid=resid, gamma=gamma, beta=beta),
                                                       2 * M * D * H, 2 * (M * H + D * H + M * D) + 8 * M * D, per_step),
-        "gemm_tc_kernel<Bias> qkv [M,256]x[256,768]": (lambda: ops.gemm(x, wqkv, ops.EPI_BIAS_BF16), 2 * M * 3 * D * D,
-                                                       2 * (M * D + 3 * D * D + M * 3 * D), per_step),
+        "gemm_tc_ares_kernel<Bias> qkv [M,256]x[256,768]": (lambda: ops.gemm(x, wqkv, ops.EPI_BIAS_BF16), 2 * M * 3 * D * D,
+                                                            2 * (M * D + 3 * D * D + M * 3 * D), per_step),
         "wgrad_tc_kernel dW13 [1376,M]x[M,256]": (lambda: ops.wgrad(dab, x, gw13, dst1=gw13b, row_map=1, rows_valid=684),
                                                   2 * M * 2 * H * D, 2 * (M * 2 * H + M * D) + 4 * 2 * 684 * D, per_step),
         "gemm_tc_kernel<Bias> dgrad [M,1376]x[1376,256]": (lambda: ops.gemm(dab, w13.t().contiguous(), ops.EPI_BIAS_BF16),
@@ -201,6 +205,8 @@ def dominant_kernel_roofline(batch: int, pk):
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"]}
     roof.update(kernel=name, us_per_launch=r["t"] * 1e6, traffic=ncu_traffic(name), peak_source=pk["src"],
                 algorithmic_bytes=r["bytes"], algorithmic_flops=r["flops"],
+                note="write-only HBM streams on this part peak at ~3.9 TB/s (tools/membw.py, profiles/r01c_membw.txt); "
+                     "write-heavy epilogues are bounded by that, not by the 6.55 TB/s copy figure",
                 all_kernels={k: {"us": v["t"] * 1e6, "tflops": v["flops"] / v["t"] / 1e12, "gbs": v["bytes"] / v["t"] / 1e9}
                              for k, v in rows.items()})
     return roof

@@ -21,9 +21,9 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 for _ in range(reps):
     torch.cuda.profiler.start()
     ops.gemm(x, wqkv, ops.EPI_BIAS_BF16)                                      # qkv projection
-    ops.gemm(x, w13, ops.EPI_SWIGLU)                                          # gated up-projection
+    ops.gemm(x, w13, ops.EPI_SWIGLU, keep_ab=False)                           # gated up-projection (training path: g only)
     ops.gemm(g, w2, ops.EPI_RESID_LN, resid=resid, gamma=gamma, beta=beta)    # down-projection + residual + LN
-    ops.gemm(x, w2t, ops.EPI_DSWIGLU, ab=dab)                                 # d(gate)
+    ops.gemm(x, w2t, ops.EPI_DGATE, A2=x, B2=w13)                             # d(gate), a|b recomputed
     ops.gemm(dab, w13t, ops.EPI_BIAS_BF16)                                    # dgrad K=1376
     ops.wgrad(dab, x, gw1, dst1=gw3, row_map=1, rows_valid=684, bias0=gb1, bias1=gb3)   # dW13
     ops.wgrad(x, g, torch.zeros(D, 684, device=dev), cols_valid=684, bias0=torch.zeros(D, device=dev))  # dW2
