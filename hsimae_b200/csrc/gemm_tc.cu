@@ -86,6 +86,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -94,6 +100,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -247,13 +258,21 @@ constexpr int kStageBufBytes = 32 * 128;   // one box
 // staging boxes per epilogue warp: the gate epilogue fills two boxes at once (a|b and gate); the others reuse a
 // single box (the TMA unit has read it long before the next one is assembled), which leaves the shared memory
 // to the operand pipeline -- these GEMMs are bound by bytes in flight from L2/HBM, not by the epilogue.
-template <int EPI> struct StagingBufs { static constexpr int value = EPI == kEpiSwiGLU ? 2 : 1; };
+// The residual / LayerNorm epilogue of the two-stage (256-column) kernel rotates three boxes per warp: each is filled
+// with a residual tile by TMA, updated in place and handed back to TMA as the output tile.
+constexpr int kResidBoxes = 3;
+template <int EPI, int S = 4> struct StagingBufs {
+  static constexpr int value = EPI == kEpiSwiGLU ? 2 : (EPI == kEpiResidLN && S == 2 ? kResidBoxes : 1);
+};
 
 struct Stager {
   uint32_t base;     // smem address of this warp's two 4 KB buffers (1024-byte aligned)
   int lane;
   bool pending;      // a committed store may still be reading the buffers
   bool leader = ptx::elect_one();   // the one lane that issues (and later waits for) this warp's bulk stores
+  const CUtensorMap* tm_resid = nullptr;   // TMA-staged residual (kEpiResidLN, S == 2): fp32 [M, N], boxes of 32 x 32
+  uint64_t* rbar = nullptr;                // this warp's kResidBoxes "residual box filled" barriers
+  uint32_t rphase = 0;                     // their phase bits
   // wait until the TMA unit has finished reading every box this warp handed over
   __device__ __forceinline__ void acquire() {
     if (pending) {
@@ -402,8 +421,68 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
     const bool ln = p.gamma != nullptr;
     const float s = valid ? row_scale(p.rs, m) : 1.0f;
     float sum = 0.f;
-    // residual chunk of 32 columns, fetched one chunk ahead (the first fetch overlaps the MMA tail)
     const float* rrow = p.resid + (size_t)(valid ? m : 0) * p.ldr;
+    constexpr bool TMA_RESID = (MODE & 4) != 0;
+    const bool staged = TMA_RESID && (width & 31) == 0 && st.tm_resid != nullptr;
+    if (TMA_RESID && staged) {
+      // Residual tiles travel through the copy engine: box (c mod 3) is filled with columns [32c, 32c+32) of this warp's
+      // 32 rows two chunks ahead of its use (the first two while the tile's MMAs are still running), every thread
+      // updates its own 128-byte row in place, and the same box goes back out as the new residual stream.  No
+      // per-thread global loads remain on the critical path (they were 30 % of this kernel's stall samples).
+      const int nch = width >> 5;
+      auto issue = [&](int c) {
+        if (st.leader) {
+          const int b = c % kResidBoxes;
+          ptx::mbar_expect_tx(st.rbar + b, kStageBufBytes);
+          ptx::tma_load_2d_addr(st.base + (uint32_t)b * kStageBufBytes, st.tm_resid, st.rbar + b, c * 32, m0);
+        }
+      };
+      st.acquire();                    // every box is free again (stores of the previous tile have been read)
+      issue(0);
+      if (nch > 1) issue(1);
+      wait_acc();
+      for (int ch = 0; ch < nch; ++ch) {
+        const int b = ch % kResidBoxes, c = ch * 32;
+        const uint32_t row = st.base + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u;
+        float v[32];
+        acc.template load<32>(c, v);
+        ptx::mbar_wait(st.rbar + b, (st.rphase >> b) & 1u);
+        st.rphase ^= 1u << b;
+        if (p.bias) add_vec<32>(p.bias + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 r = ptx::ld_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4));
+          v[4 * j] = fmaf(s, v[4 * j], __uint_as_float(r.x));
+          v[4 * j + 1] = fmaf(s, v[4 * j + 1], __uint_as_float(r.y));
+          v[4 * j + 2] = fmaf(s, v[4 * j + 2], __uint_as_float(r.z));
+          v[4 * j + 3] = fmaf(s, v[4 * j + 3], __uint_as_float(r.w));
+        }
+        if (p.resid2 && valid) {
+          float r2[32];
+          load_f32_row<32>(p.resid2 + (size_t)m * p.ldr + c, r2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += r2[i];
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += v[i];
+        }
+        if (ln) acc.template store<32>(c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ptx::st_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4), pack4_f32(v + 4 * j));
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (st.leader) {
+          ptx::tma_store_2d(tmO0, st.base + (uint32_t)b * kStageBufBytes, c, m0);
+          ptx::bulk_commit();
+          // the box used one chunk ago is free once its store has been read: refill it for chunk ch + 2
+          if (ch + 2 < nch) ptx::bulk_wait_read1();
+        }
+        st.pending = true;
+        if (ch + 2 < nch) issue(ch + 2);
+      }
+    } else {
+    // residual chunk of 32 columns, fetched one chunk ahead (the first fetch overlaps the MMA tail)
     float rnext[32];   // only live when PREFETCH
     if constexpr (PREFETCH) { if (width >= 32) load_f32_row<32>(rrow, rnext); }
     wait_acc();
@@ -440,6 +519,8 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
     int c = 0;
     for (; c + 32 <= width; c += 32) pass1(std::integral_constant<int, 32>{}, c);
     for (; c + 16 <= width; c += 16) pass1(std::integral_constant<int, 16>{}, c);
+    }
+    int c = 0;
     if (ln) {
       acc.fence_store();
       const float inv = 1.0f / (float)width;
@@ -529,13 +610,14 @@ constexpr int kSmemBudget = 200 * 1024;
 template <int EPI, int S, int P>
 __global__ void __launch_bounds__(64 + 128 * S, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, GemmArgs p,
-               int block_n, int stages, int n_blks, int num_tiles) {
+               const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+               const __grid_constant__ CUtensorMap tmR, GemmArgs p, int block_n, int stages, int n_blks, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   constexpr uint32_t kAccStride = 512 / S;
-  constexpr uint32_t kStagingBytes = 4 * S * StagingBufs<EPI>::value * kStageBufBytes;
+  constexpr uint32_t kStagingBytes = 4 * S * StagingBufs<EPI, S>::value * kStageBufBytes;
+  constexpr bool kTmaResid = EPI == kEpiResidLN && S == 2;
 
   const uint32_t b_bytes = (uint32_t)(block_n / P) * 128u;   // this CTA's share of the weight tile
   const uint32_t stage_bytes = kATileBytes + b_bytes;
@@ -544,7 +626,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
   uint64_t* tempty = tfull + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + S);
+  uint64_t* rbar = tempty + S;                                   // [4 * S][kResidBoxes], only used when kTmaResid
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + (kTmaResid ? 4 * S * kResidBoxes : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -557,8 +640,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmB);
     ptx::prefetch_tmap(&tmO0);
     ptx::prefetch_tmap(&tmO1);
+    if constexpr (kTmaResid) ptx::prefetch_tmap(&tmR);
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
     for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128 * P); }
+    if constexpr (kTmaResid) { for (int i = 0; i < 4 * S * kResidBoxes; ++i) ptx::mbar_init(rbar + i, 1); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -631,7 +716,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;   // accumulator stage served by this warp's group
-    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI>::value * kStageBufBytes), lane, false};
+    Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI, S>::value * kStageBufBytes), lane, false};
+    if constexpr (kTmaResid) { st.tm_resid = &tmR; st.rbar = rbar + (warp - 2) * kResidBoxes; }
     const uint32_t tempty_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(tempty + grp), 0) : 0u;
     int it = grp;
     TR_DECL;
@@ -641,7 +727,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
       const int n0 = n_blk * block_n;
       int width = p.N - n0; if (width > block_n) width = block_n;
-      TR_WAIT(1, tc_epilogue<EPI, (S == 2 ? 1 : 0)>(p, acc, st, &tmO0, &tmO1, (m_blk * P + crank) * kBlockM + q * 32, lane, n0, width,
+      TR_WAIT(1, tc_epilogue<EPI, (S == 2 ? 1 : 0) | (kTmaResid ? 4 : 0)>(p, acc, st, &tmO0, &tmO1, (m_blk * P + crank) * kBlockM + q * 32, lane, n0, width,
                        [&]() { TR_WAIT(0, ptx::mbar_wait(tfull + grp, aphase)); ptx::tc_fence_after(); }));
       ptx::tc_fence_before();
       if constexpr (P == 2) ptx::mbar_arrive_cluster(tempty_addr); else ptx::mbar_arrive(tempty + grp);
@@ -1343,12 +1429,13 @@ int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_b
     configured = true;
   }
   // shared memory: [operand pipeline stages][epilogue staging boxes][barriers]; as many stages as fit
-  const int staging = 4 * S * StagingBufs<EPI>::value * kStageBufBytes;
+  const int staging = 4 * S * StagingBufs<EPI, S>::value * kStageBufBytes;
   const int stage_bytes = kATileBytes + block_n / P * 128;
   const int num_kb = ceil_div(a.K, kBlockK);
   // epilogues that read per-row global inputs (saved pre-activations, residual) rely on L1 to merge each thread's
-  // 16-byte loads of one line: leave ~36 KB of the 228 KB shared/L1 array to the cache for them
-  const int smem_cap = (EPI == kEpiDSwiGLU || EPI == kEpiResidLN) ? kSmemMax - 36 * 1024 : kSmemMax;
+  // 16-byte loads of one line: leave ~36 KB of the 228 KB shared/L1 array to the cache for them (the two-stage
+  // residual epilogue stages its rows through TMA instead)
+  const int smem_cap = (EPI == kEpiDSwiGLU || (EPI == kEpiResidLN && S != 2)) ? kSmemMax - 36 * 1024 : kSmemMax;
   int stages = (smem_cap - staging - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > 2 * num_kb) stages = 2 * num_kb;
@@ -1357,7 +1444,7 @@ int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_b
   HS_REQUIRE(smem <= (size_t)kSmemMax, "gemm: tile N=%d needs %zu bytes of shared memory", block_n, smem);
   const int num_tiles = ceil_div(m_blks, P) * n_blks;
   HS_TRY(launch_clustered(gemm_tc_kernel<EPI, S, P>, pair_grid(num_tiles, P), 64 + 128 * S, smem, P, stream, tm[0], tm[1], tm[2],
-                          tm[3], a, block_n, stages, n_blks, num_tiles));
+                          tm[3], tm[4], a, block_n, stages, n_blks, num_tiles));
   HS_CHECK_LAUNCH("gemm_tc_kernel");
   return kOk;
 }
@@ -1497,10 +1584,13 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   const int n_blks = ceil_div(a.N, block_n);
   const int m_blks = ceil_div(a.M, kBlockM);
   const bool ares = use_ares(a, epi, block_n, n_blks);
-  const bool pair = use_pair(block_n, m_blks, a.K, ares, epi == kEpiSwiGLU && a.out0 == nullptr);
-  CUtensorMap tm[4];
+  // the 256-column residual epilogue keeps 96 KB of residual boxes: only a pair's half-size weight tiles leave a useful ring
+  const bool pair = use_pair(block_n, m_blks, a.K, ares, epi == kEpiSwiGLU && a.out0 == nullptr) ||
+                    (epi == kEpiResidLN && block_n > 128 && block_n % 32 == 0 && m_blks >= 2 && use_pair(block_n, m_blks, 512, false, false));
+  CUtensorMap tm[5];
   HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tm[0]));
   HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(pair ? block_n / 2 : block_n), &tm[1]));
+  tm[4] = tm[0];   // residual map: only the residual / LayerNorm epilogue has one
   // output boxes: [32 rows x 128 bytes]
   const uint64_t M = (uint64_t)a.M, N = (uint64_t)a.N;
   switch (epi) {
@@ -1516,6 +1606,7 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
       HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 32, 32, &tm[2], 4));
       if (a.gamma) HS_TRY(get_tmap(a.out1, N, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
       else tm[3] = tm[2];
+      HS_TRY(get_tmap(a.resid, N, M, (uint64_t)a.ldr, 32, 32, &tm[4], 4));
       return launch_gemm<kEpiResidLN>(a, tm, block_n, n_blks, m_blks, false, pair, stream);
     case kEpiSwiGLU:
       HS_TRY(get_tmap(a.out1, N / 2, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
