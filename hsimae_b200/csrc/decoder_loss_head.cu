@@ -323,28 +323,48 @@ int launch_head_bwd(const HeadArgs& a, cudaStream_t stream) {
 // orientations, fused q|k|v and interleaved w1|w3) + fp32 bias/affine arena.
 // One launch over a device-resident job table.
 // ---------------------------------------------------------------------------
+// One CTA per [32 rows x 64 cols] tile of one job (1-D launch over all tiles; the tile -> job map follows the job
+// table): coalesced fp32 reads, coalesced writes in either orientation (the transposed copy goes through shared
+// memory so that the 32 destination elements of a source column leave as one 64-byte run).
 __global__ void __launch_bounds__(256)
-pack_kernel(const PackJob* __restrict__ jobs, __nv_bfloat16* __restrict__ wb, float* __restrict__ wf) {
-  const PackJob j = jobs[blockIdx.y];
-  const int total = j.rows * j.cols;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r = i / j.cols, c = i - r * j.cols;
+pack_kernel(const PackJob* __restrict__ jobs, const int* __restrict__ tile_job, __nv_bfloat16* __restrict__ wb, float* __restrict__ wf) {
+  __shared__ float tile[kPackTileR][kPackTileC + 1];
+  const PackJob j = jobs[tile_job[blockIdx.x]];
+  const int t = blockIdx.x - j.tile0;
+  const int r0 = (t / j.tiles_c) * kPackTileR, c0 = (t % j.tiles_c) * kPackTileC;
+  auto dst_row = [&](int r) {
     int rm = r;
     if (j.row_map != 0) rm = (r / 16) * 32 + (j.row_map - 1) * 16 + (r % 16);
-    rm += j.row_off;
-    const float v = j.src[i];
-    if (j.kind == 0) wf[j.dst_off + (int64_t)rm * j.pitch + c] = v;
-    else if (j.kind == 1) wb[j.dst_off + (int64_t)rm * j.pitch + c] = __float2bfloat16_rn(v);
-    else wb[j.dst_off + (int64_t)c * j.pitch + rm] = __float2bfloat16_rn(v);
+    return rm + j.row_off;
+  };
+  if (j.kind != 2) {
+    for (int i = threadIdx.x; i < kPackTileR * kPackTileC; i += blockDim.x) {
+      const int r = r0 + i / kPackTileC, c = c0 + i % kPackTileC;
+      if (r < j.rows && c < j.cols) {
+        const float v = j.src[(size_t)r * j.cols + c];
+        if (j.kind == 0) wf[j.dst_off + (int64_t)dst_row(r) * j.pitch + c] = v;
+        else wb[j.dst_off + (int64_t)dst_row(r) * j.pitch + c] = __float2bfloat16_rn(v);
+      }
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < kPackTileR * kPackTileC; i += blockDim.x) {
+    const int lr = i / kPackTileC, lc = i % kPackTileC;
+    const int r = r0 + lr, c = c0 + lc;
+    tile[lr][lc] = (r < j.rows && c < j.cols) ? j.src[(size_t)r * j.cols + c] : 0.f;
+  }
+  __syncthreads();
+  // destination rows (mapped source rows) are the fast index of the transposed copy
+  for (int i = threadIdx.x; i < kPackTileR * kPackTileC; i += blockDim.x) {
+    const int lc = i / kPackTileR, lr = i % kPackTileR;
+    const int r = r0 + lr, c = c0 + lc;
+    if (r < j.rows && c < j.cols) wb[j.dst_off + (int64_t)c * j.pitch + dst_row(r)] = __float2bfloat16_rn(tile[lr][lc]);
   }
 }
 
-int launch_pack(const PackJob* jobs_dev, int njobs, int max_elems, __nv_bfloat16* bf16_arena, float* f32_arena, cudaStream_t stream) {
-  if (njobs == 0) return kOk;
-  int gx = ceil_div(max_elems, 256 * 8);
-  if (gx < 1) gx = 1;
-  if (gx > 64) gx = 64;
-  pack_kernel<<<dim3(gx, njobs), 256, 0, stream>>>(jobs_dev, bf16_arena, f32_arena);
+int launch_pack(const PackJob* jobs_dev, int njobs, int ntiles, __nv_bfloat16* bf16_arena, float* f32_arena, cudaStream_t stream) {
+  if (njobs == 0 || ntiles == 0) return kOk;
+  pack_kernel<<<ntiles, 256, 0, stream>>>(jobs_dev, reinterpret_cast<const int*>(jobs_dev + njobs), bf16_arena, f32_arena);
   HS_CHECK_LAUNCH("pack_kernel");
   return kOk;
 }

@@ -87,7 +87,11 @@ struct Builder {
     p->jobs.push_back(JobT{slot, dst, rows, cols, pitch, kind, row_map, row_off});
     if (rows * cols > p->max_job_elems) p->max_job_elems = rows * cols;
   }
-  void vec(int slot, int64_t dst, int n, int row_map = 0, int row_off = 0) { job(slot, dst, n, 1, 1, 0, row_map, row_off); }
+  void vec(int slot, int64_t dst, int n, int row_map = 0, int row_off = 0) {
+    // plain vectors are packed as one row (64 elements per tile column block instead of one element per tile row)
+    if (row_map == 0) job(slot, dst + row_off, 1, n, n, 0, 0, 0);
+    else job(slot, dst, n, 1, 1, 0, row_map, row_off);
+  }
 
   BlockW block(const std::string& pre, int d, int H, int Hp, bool qkv_bias) {
     BlockW w{};
@@ -514,7 +518,15 @@ int hsimae_plan_param_has_grad(const hsimae_plan* p, int i) { return (p && i >= 
 int64_t hsimae_plan_grad_arena_elems(const hsimae_plan* p) { return p ? p->grad_elems : 0; }
 int64_t hsimae_plan_bf16_arena_elems(const hsimae_plan* p) { return p ? p->bf16_elems : 0; }
 int64_t hsimae_plan_f32_arena_elems(const hsimae_plan* p) { return p ? p->f32_elems : 0; }
-int64_t hsimae_plan_pack_table_bytes(const hsimae_plan* p) { return p ? (int64_t)(p->jobs.size() * sizeof(PackJob)) : 0; }
+namespace {
+int job_tiles_c(const JobT& t) { return ceil_div(t.cols, kPackTileC); }
+int job_tiles(const JobT& t) { return ceil_div(t.rows, kPackTileR) * job_tiles_c(t); }
+int pack_tiles(const hsimae_plan* p) { int n = 0; for (const JobT& t : p->jobs) n += job_tiles(t); return n; }
+}  // namespace
+// device table: the jobs followed by the tile -> job map
+int64_t hsimae_plan_pack_table_bytes(const hsimae_plan* p) {
+  return p ? (int64_t)(p->jobs.size() * sizeof(PackJob) + (size_t)pack_tiles(p) * sizeof(int)) : 0;
+}
 int hsimae_plan_grad_bucket(const hsimae_plan* p, int i, int64_t* offset, int64_t* elems) {
   HS_REQUIRE(p && offset && elems && i >= 0 && i < 4, "grad_bucket: bad argument");
   const int64_t begin = i == 0 ? 0 : p->bucket_end[i - 1];
@@ -531,17 +543,22 @@ int hsimae_pack_params(hsimae_plan* p, const void* const* params, void* bf16_are
   if (same) for (size_t i = 0; i < np; ++i) if (p->last_ptrs[i] != params[i]) { same = false; break; }
   if (!same) {
     std::vector<PackJob> jobs(p->jobs.size());
+    std::vector<int> tile_job;
     for (size_t i = 0; i < jobs.size(); ++i) {
       const JobT& t = p->jobs[i];
       HS_REQUIRE(params[t.slot] != nullptr, "parameter '%s' is missing", p->slots[t.slot].name.c_str());
-      jobs[i] = PackJob{(const float*)params[t.slot], t.dst_off, t.rows, t.cols, t.pitch, t.kind, t.row_map, t.row_off};
+      jobs[i] = PackJob{(const float*)params[t.slot], t.dst_off, t.rows, t.cols, t.pitch, t.kind, t.row_map, t.row_off,
+                        (int)tile_job.size(), job_tiles_c(t)};
+      tile_job.insert(tile_job.end(), (size_t)job_tiles(t), (int)i);
     }
     HS_CHECK_CUDA(cudaMemcpyAsync(table, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    HS_CHECK_CUDA(cudaMemcpyAsync(static_cast<char*>(table) + jobs.size() * sizeof(PackJob), tile_job.data(), tile_job.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice, st));
     HS_CHECK_CUDA(cudaStreamSynchronize(st));  // `jobs` is a stack-owned staging buffer
     p->last_ptrs.assign(params, params + np);
     p->last_table = table;
   }
-  return launch_pack((const PackJob*)table, (int)p->jobs.size(), p->max_job_elems, (bf16*)bf16_arena, (float*)f32_arena, st);
+  return launch_pack((const PackJob*)table, (int)p->jobs.size(), pack_tiles(p), (bf16*)bf16_arena, (float*)f32_arena, st);
 }
 
 int hsimae_mask(const float* noise_t, const float* noise_l, int32_t n, int32_t T, int32_t L, int32_t len_t, int32_t len_l,

@@ -150,7 +150,11 @@ struct PackJob {
   int kind;          // 0: fp32 copy, 1: bf16, 2: bf16 transposed
   int row_map;       // 0: plain, 1: w1-interleave (which=0), 2: w3-interleave (which=1)
   int row_off;       // added to the (mapped) row
+  int tile0;         // index of this job's first [32 x 64] tile in the launch
+  int tiles_c;       // tiles per tile row
 };
-int launch_pack(const PackJob* jobs_dev, int njobs, int max_elems, __nv_bfloat16* bf16_arena, float* f32_arena, cudaStream_t stream);
+constexpr int kPackTileR = 32, kPackTileC = 64;
+// the device table is [njobs] PackJob followed by [ntiles] int32 tile -> job
+int launch_pack(const PackJob* jobs_dev, int njobs, int ntiles, __nv_bfloat16* bf16_arena, float* f32_arena, cudaStream_t stream);
 
 }  // namespace hsimae
