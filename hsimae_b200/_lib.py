@@ -87,6 +87,7 @@ PROTOTYPES = {
                                          c_i32, c_void_p]),
     "hsimae_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32,
                                           c_i32, c_i32, c_i32, c_i32, c_void_p]),
+    "hsimae_gather_patches": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
 }
 
 _lib = None

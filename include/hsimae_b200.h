@@ -161,6 +161,16 @@ int hsimae_attention_backward(const void* qkv, const void* out, const float* lse
                               int32_t D, int32_t heads, int32_t K, int32_t nseq, int32_t len, int32_t seq_step,
                               int32_t tok_step, void* stream);
 
+/* ---- on-device pretraining data feed -------------------------------------------------------------
+ * Replaces HSIdataset4PT.__getitem__ + DataLoader collation (/root/reference/Model_Pretraining.py:40-51, :76):
+ *   out[i, 0, c, y, x] = (scene[num][h + y', w + x', c] - min) / (max - min),  (c_, h, w, num, max, min) = cut_info[index[i]]
+ * with y' = img-1-y when flips[2i+1] (np.flip(data, 0)) and x' = img-1-x when flips[2i] (np.flip(data, 1)).
+ * scenes: all scenes back to back, each [H, W, bands] fp32; scene_off[s] = element offset of scene s, scene_hw[2s..] = (H, W);
+ * cut_info: int16 rows of 6 (Utils/Preprocessing.py:78,114); index: int64 [n]; flips: uint8 [n, 2] or NULL (no flips);
+ * out: fp32 [n, 1, bands, img, img].  Windows must lie inside their scene (the host wrapper checks once). */
+int hsimae_gather_patches(const float* scenes, const int64_t* scene_off, const int32_t* scene_hw, int32_t bands, int32_t img,
+                          const int16_t* cut_info, const int64_t* index, const uint8_t* flips, int32_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
