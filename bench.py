@@ -84,7 +84,11 @@ def cpu_step_fn(batch: int):
     no_decay = ("bias", "norm")
     groups = [{"params": [p for n, p in leaves.items() if p.requires_grad and not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
               {"params": [p for n, p in leaves.items() if p.requires_grad and any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
-    opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    if args.fused_optimizer:
+        from hsimae_b200.optim import FusedAdamW
+        opt = FusedAdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    else:
+        opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
     x = torch.randn(batch, 1, 32, 9, 9)
 
     def step():
@@ -149,7 +153,7 @@ def ncu_traffic(cand: str):
     tools/prof_kernels.py run at the shapes timed here), or None"""
     path = os.path.join(ROOT, "profiles", "r01c_ncu_full_kernels.json")
     want = {"gemm_tc_dgate_kernel": "d(gate)", "gemm_tc_ares_kernel<SwiGLU": "gated up-projection", "gemm_tc_kernel<ResidLN>": "down-projection",
-            "gemm_tc_ares_kernel<Bias> qkv": "qkv projection", "wgrad_tc_kernel dW13": "wgrad dW13", "gemm_tc_kernel<Bias> dgrad": "dgrad K=1376"}
+            "gemm_tc_kernel<Bias> qkv": "qkv projection", "wgrad_tc_kernel dW13": "wgrad dW13", "gemm_tc_kernel<Bias> dgrad": "dgrad K=1376"}
     try:
         rows = json.load(open(path))
         for key, label in want.items():
@@ -183,7 +187,7 @@ def dominant_kernel_roofline(batch: int, pk):
             lambda: ops.gemm(x, w13, ops.EPI_SWIGLU, keep_ab=False), 2 * M * 2 * H * D, 2 * (M * D + 2 * H * D + M * H), per_step),
         "gemm_tc_kernel<ResidLN> [M,688]x[688,256]": (lambda: ops.gemm(g, w2, ops.EPI_RESID_LN, resid=resid, gamma=gamma, beta=beta),
                                                       2 * M * D * H, 2 * (M * H + D * H + M * D) + 8 * M * D, per_step),
-        "gemm_tc_ares_kernel<Bias> qkv [M,256]x[256,768]": (lambda: ops.gemm(x, wqkv, ops.EPI_BIAS_BF16), 2 * M * 3 * D * D,
+        "gemm_tc_kernel<Bias> qkv [M,256]x[256,768]": (lambda: ops.gemm(x, wqkv, ops.EPI_BIAS_BF16), 2 * M * 3 * D * D,
                                                             2 * (M * D + 3 * D * D + M * 3 * D), per_step),
         "wgrad_tc_kernel dW13 [1376,M]x[M,256]": (lambda: ops.wgrad(dab, x, gw13, dst1=gw13b, row_map=1, rows_valid=684),
                                                   2 * M * 2 * H * D, 2 * (M * 2 * H + M * D) + 4 * 2 * 684 * D, per_step),
@@ -224,6 +228,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop (for ncu)")
+    ap.add_argument("--fused-optimizer", action="store_true",
+                    help="opt-in hsimae_b200.optim.FusedAdamW instead of the driver's torch.optim.AdamW (SURVEY 8f-3; not the default metric)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)
@@ -251,7 +257,11 @@ def main():
     no_decay = ["bias", "norm"]
     groups = [{"params": [p for n, p in model.named_parameters() if not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
               {"params": [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
-    opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    if args.fused_optimizer:
+        from hsimae_b200.optim import FusedAdamW
+        opt = FusedAdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    else:
+        opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
     torch.manual_seed(1000 + rank); random.seed(7)   # python RNG identical on all ranks (same visible shape), data differs
     B = args.batch
     pool = [torch.randn(B, 1, 32, 9, 9, device=dev) for _ in range(4)]
@@ -351,7 +361,7 @@ def main():
                                        f"batch {B} synthetic 9x9x32 patches per GPU (BASELINE.json configs[1])",
                            "global_batch": world * B, "parallelism": f"dp{world}",
                            "l2": "4 rotating input batches; per-step activation working set (~15 GB) >> 126 MB L2",
-                           "optimizer": "torch.optim.AdamW (driver-owned, unchanged)"},
+                           "optimizer": "hsimae_b200.optim.FusedAdamW (opt-in)" if args.fused_optimizer else "torch.optim.AdamW (driver-owned, unchanged)"},
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": B * CUBE * 4,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps},
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "loss": last_loss,

@@ -87,6 +87,8 @@ PROTOTYPES = {
                                          c_i32, c_void_p]),
     "hsimae_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32,
                                           c_i32, c_i32, c_i32, c_i32, c_void_p]),
+    "hsimae_adamw_tile_elems": (c_i32, []),
+    "hsimae_adamw_step": (c_int, [c_void_p, c_i32, c_i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_void_p]),
     "hsimae_gather_patches": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
 }
 
