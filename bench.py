@@ -84,11 +84,7 @@ def cpu_step_fn(batch: int):
     no_decay = ("bias", "norm")
     groups = [{"params": [p for n, p in leaves.items() if p.requires_grad and not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
               {"params": [p for n, p in leaves.items() if p.requires_grad and any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
-    if args.fused_optimizer:
-        from hsimae_b200.optim import FusedAdamW
-        opt = FusedAdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
-    else:
-        opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
     x = torch.randn(batch, 1, 32, 9, 9)
 
     def step():
