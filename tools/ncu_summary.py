@@ -4,7 +4,7 @@ usage: python tools/ncu_summary.py gpurun_out/prof_kernels.ncu-rep profiles/r01c
 The labels are the launch order of tools/prof_kernels.py (torch's own fill kernels are skipped)."""
 import csv, io, json, subprocess, sys
 
-LABELS = ["qkv projection (A-resident, bias)", "gated up-projection, g only (A-resident, SwiGLU)", "down-projection + residual + LayerNorm",
+LABELS = ["qkv projection (streaming pair kernel, bias)", "gated up-projection, g only (A-resident, SwiGLU)", "down-projection + residual + LayerNorm (TMA-staged residual)",
           "d(gate) with recomputed a|b (dual GEMM)", "dgrad K=1376 (pair)", "wgrad dW13 (pair)", "wgrad dW2",
           "attention fwd fusion (len 18)", "attention bwd fusion (len 18)", "attention fwd spatial", "attention fwd spectral"]
 
