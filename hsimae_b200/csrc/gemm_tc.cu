@@ -1490,6 +1490,9 @@ bool use_pair(int block_n, int m_blks, int K, int N, bool ares, bool light_epilo
   static const int mode = getenv("HSIMAE_GEMM_PAIR") ? atoi(getenv("HSIMAE_GEMM_PAIR")) : 1;
   if (mode == 0 || block_n % 32 != 0 || m_blks < 2) return false;
   if (mode >= 2) return true;
+  // less than one row block per SM: nothing streams long enough for the halved weight tiles to matter, and the
+  // cluster launch / cross-CTA handshakes only add latency (small fine-tuning and inference batches)
+  if (m_blks < kNumSMs) return false;
   // A-resident kernels stream their weight tiles at the per-SM L2 read rate (~42 B/clk); halving them pays once the
   // epilogue is light (gated projection that does not keep a|b: 62 -> 58 us), not when it is the limit anyway
   if (ares) return light_epilogue;
@@ -1580,7 +1583,7 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   if (epi == kEpiDGate) {
     static const int pair_mode = getenv("HSIMAE_GEMM_PAIR") ? atoi(getenv("HSIMAE_GEMM_PAIR")) : 1;
     // pairs halve the weight tiles in shared memory, which is what leaves room for a useful ring next to two A blocks
-    if (pair_mode != 0 && a.M > kBlockM) return launch_gemm_dgate<2>(a, stream);
+    if (pair_mode != 0 && (a.M > kBlockM * kNumSMs || (pair_mode >= 2 && a.M > kBlockM))) return launch_gemm_dgate<2>(a, stream);
     return launch_gemm_dgate<1>(a, stream);
   }
   const int block_n = pick_block_n(a.N, a.K, epi);
@@ -1691,7 +1694,7 @@ int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
   HS_TRY(wgrad_check_args(a));
   // CTA pairs halve the L2 reads of X (re-read by every row tile); they need at least two row tiles' worth of rows
   static const int pair = env_int("HSIMAE_WGRAD_PAIR", 1);
-  if (pair != 0 && a.Nout > 2 * kBlockM) return launch_wgrad<2>(a, stream);
+  if (pair != 0 && a.Nout > 2 * kBlockM && a.Mred >= 64 * kNumSMs) return launch_wgrad<2>(a, stream);
   return launch_wgrad<1>(a, stream);
 }
 
