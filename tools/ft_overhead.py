@@ -31,3 +31,6 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 ev = prof.key_averages()
 tot = sum(e.device_time_total for e in ev) / 3 / 1e3
 print("sum of kernel durations %.2f ms/step over %d launches/step" % (tot, sum(e.count for e in ev) / 3))
+rows = sorted(ev, key=lambda e: -e.device_time_total)[:18]
+for e in rows:
+    print("%8.1f us/step  n=%5.1f  avg %6.1f us  %s" % (e.device_time_total / 3, e.count / 3, e.device_time_total / max(e.count, 1), e.key[:90]))
