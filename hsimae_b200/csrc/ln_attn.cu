@@ -478,6 +478,17 @@ bool attn_mma_supported(const AttnArgs& a);
 int launch_attn_mma_fwd(const AttnArgs& a, cudaStream_t stream);
 int launch_attn_mma_bwd(const AttnArgs& a, cudaStream_t stream);
 
+bool attn_small_supported(const AttnArgs& a);
+int launch_attn_small(const AttnArgs& a, bool bwd, cudaStream_t stream);
+
+// groups of at most 4 tokens (spectral encoder): one thread per (sequence, head), attn_small.cu
+// (HSIMAE_ATTN_SMALL=0 sends them through the block-diagonal mma path instead, for A/B measurements)
+static bool attn_use_small(const AttnArgs& a) {
+  static const bool off = getenv("HSIMAE_ATTN_SMALL") && atoi(getenv("HSIMAE_ATTN_SMALL")) == 0;
+  static const bool force_simt = getenv("HSIMAE_ATTN_SIMT") && atoi(getenv("HSIMAE_ATTN_SIMT")) != 0;
+  return !off && !force_simt && attn_small_supported(a);
+}
+
 // HSIMAE_ATTN_SIMT=1 forces the CUDA-core kernels (kept for groups longer than 40 tokens and as an A/B checker)
 static bool attn_use_mma(const AttnArgs& a) {
   static const bool force_simt = getenv("HSIMAE_ATTN_SIMT") && atoi(getenv("HSIMAE_ATTN_SIMT")) != 0;
@@ -487,6 +498,7 @@ static bool attn_use_mma(const AttnArgs& a) {
 int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream) {
   HS_TRY(attn_check(a));
   if (a.N == 0) return kOk;
+  if (attn_use_small(a)) return launch_attn_small(a, false, stream);
   if (attn_use_mma(a)) return launch_attn_mma_fwd(a, stream);
   switch (a.D / a.heads) {
     case 8: return attn_fwd_launch<8>(a, stream);
@@ -499,6 +511,7 @@ int launch_attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   HS_TRY(attn_check(a));
   HS_REQUIRE(a.lse && a.dout && a.dqkv, "attention bwd: missing buffers");
   if (a.N == 0) return kOk;
+  if (attn_use_small(a)) return launch_attn_small(a, true, stream);
   if (attn_use_mma(a)) return launch_attn_mma_bwd(a, stream);
   switch (a.D / a.heads) {
     case 8: return attn_bwd_launch<8>(a, stream);
