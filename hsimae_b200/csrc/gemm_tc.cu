@@ -53,6 +53,11 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+// Programmatic dependent launch: kernels launched with the programmatic-stream-serialization attribute may start their
+// prologue (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel on the stream drains;
+// pdl_wait() blocks until that kernel has completed and its writes are visible, pdl_trigger() lets the next one go.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -650,11 +655,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
     else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // everything above touched only this CTA's shared / tensor memory
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -736,6 +743,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2 && lane == 0) TR_DUMP(2);
   }
 
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();   // nobody leaves while the peer may still read its shared memory / barriers
@@ -798,11 +806,13 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
     else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // everything above touched only this CTA's shared / tensor memory
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -904,6 +914,7 @@ gemm_tc_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 2 && lane == 0) TR_DUMP(2);
   }
 
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();
@@ -969,11 +980,13 @@ gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
     else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // everything above touched only this CTA's shared / tensor memory
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -1114,6 +1127,7 @@ gemm_tc_dgate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 2 && lane == 0) TR_DUMP(2);
   }
 
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();
@@ -1181,11 +1195,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
     else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // everything above touched only this CTA's shared / tensor memory
 
   if (nkb > 0) {
     if (warp == 0) {
@@ -1276,6 +1292,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     }
   }
 
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (P == 2) ptx::cluster_sync_all();
@@ -1406,10 +1423,13 @@ template <class Kernel, class... Args>
 int launch_clustered(Kernel kernel, int grid, int threads, size_t smem, int P, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = !(getenv("HSIMAE_PDL") && atoi(getenv("HSIMAE_PDL")) == 0);
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
   HS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
   return kOk;
 }
