@@ -218,6 +218,7 @@ template <int HD, int NT>
 __global__ void __launch_bounds__(kAttnThreads, 4)
 attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_wait();
   const int D = a.D, K = a.s.K, H = a.heads;
   const int pitch = 3 * D * 2 + 16;                       // +16 B: ldmatrix rows land in distinct bank groups
   uint8_t* sq = smraw;                                    // [spc*K][pitch]
@@ -297,6 +298,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
       for (int i = threadIdx.x; i < ns * K * H; i += blockDim.x) ldst[i] = slse[i];
     }
   }
+  pdl_trigger();
 }
 
 // ---------------------------------------------------------------------------
@@ -307,6 +309,7 @@ template <int HD, int NT>
 __global__ void __launch_bounds__(kAttnThreads, 3)
 attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_wait();
   const int D = a.D, K = a.s.K, H = a.heads;
   const int pitch = 3 * D * 2 + 16;
   const int pitch_o = D * 2 + 16;
@@ -425,6 +428,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
       dst[i] = *reinterpret_cast<const uint4*>(sdq + (size_t)r * pitch + c * 16);
     }
   }
+  pdl_trigger();
 }
 
 int host_units_per_head(const SeqSpec& q) {
@@ -451,7 +455,7 @@ int fwd_launch_nt(const AttnArgs& a, cudaStream_t stream) {
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
   if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
-  attn_mma_fwd_kernel<HD, NT><<<grid, kAttnThreads, smem, stream>>>(a, spc, pick_hgroups(a.heads, spc, host_units_per_head(a.s)));
+  HS_CHECK_CUDA(launch_pdl(attn_mma_fwd_kernel<HD, NT>, dim3(grid), dim3(kAttnThreads), smem, stream, a, spc, pick_hgroups(a.heads, spc, host_units_per_head(a.s))));
   HS_CHECK_LAUNCH("attn_mma_fwd_kernel");
   return kOk;
 }
@@ -468,7 +472,7 @@ int bwd_launch_nt(const AttnArgs& a, cudaStream_t stream) {
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
   if (grid > 6 * kNumSMs) grid = 6 * kNumSMs;
-  attn_mma_bwd_kernel<HD, NT><<<grid, kAttnThreads, smem, stream>>>(a, spc, pick_hgroups(a.heads, spc, host_units_per_head(a.s)));
+  HS_CHECK_CUDA(launch_pdl(attn_mma_bwd_kernel<HD, NT>, dim3(grid), dim3(kAttnThreads), smem, stream, a, spc, pick_hgroups(a.heads, spc, host_units_per_head(a.s))));
   HS_CHECK_LAUNCH("attn_mma_bwd_kernel");
   return kOk;
 }

@@ -51,6 +51,7 @@ template <int HD, int LEN>
 __global__ void __launch_bounds__(kSmallThreads)
 attn_small_fwd_kernel(AttnArgs a, int spc) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_wait();
   const int D = a.D, K = a.s.K, H = a.heads;
   const int pitch = 3 * D * 2 + 16;
   uint8_t* sq = smraw;                                                   // [spc*K][pitch]
@@ -117,6 +118,7 @@ attn_small_fwd_kernel(AttnArgs a, int spc) {
       for (int i = threadIdx.x; i < ns * K * H; i += blockDim.x) ldst[i] = slse[i];
     }
   }
+  pdl_trigger();
 }
 
 // ---------------------------------------------------------------------------
@@ -127,6 +129,7 @@ template <int HD, int LEN>
 __global__ void __launch_bounds__(kSmallThreads)
 attn_small_bwd_kernel(AttnArgs a, int spc) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  pdl_wait();
   const int D = a.D, K = a.s.K, H = a.heads;
   const int pitch = 3 * D * 2 + 16, pitch_o = 2 * D * 2 + 16;
   uint8_t* sq = smraw;                                               // [spc*K][pitch]   q|k|v  -> overwritten with dq|dk|dv
@@ -212,6 +215,7 @@ attn_small_bwd_kernel(AttnArgs a, int spc) {
       dst[i] = *reinterpret_cast<const uint4*>(sq + (size_t)r * pitch + c * 16);
     }
   }
+  pdl_trigger();
 }
 
 template <int HD, int LEN>
@@ -226,7 +230,7 @@ int small_fwd(const AttnArgs& a, cudaStream_t stream) {
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<HD, LEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
   if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
-  attn_small_fwd_kernel<HD, LEN><<<grid, kSmallThreads, smem, stream>>>(a, spc);
+  HS_CHECK_CUDA(launch_pdl(attn_small_fwd_kernel<HD, LEN>, dim3(grid), dim3(kSmallThreads), smem, stream, a, spc));
   HS_CHECK_LAUNCH("attn_small_fwd_kernel");
   return kOk;
 }
@@ -243,7 +247,7 @@ int small_bwd(const AttnArgs& a, cudaStream_t stream) {
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<HD, LEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
   if (grid > 6 * kNumSMs) grid = 6 * kNumSMs;
-  attn_small_bwd_kernel<HD, LEN><<<grid, kSmallThreads, smem, stream>>>(a, spc);
+  HS_CHECK_CUDA(launch_pdl(attn_small_bwd_kernel<HD, LEN>, dim3(grid), dim3(kSmallThreads), smem, stream, a, spc));
   HS_CHECK_LAUNCH("attn_small_bwd_kernel");
   return kOk;
 }

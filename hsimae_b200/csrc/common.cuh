@@ -1,5 +1,6 @@
 // Shared device/host helpers for the hsimae_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -36,6 +37,25 @@ const char* last_error();
       return ::hsimae::kCudaError;                                                      \
     }                                                                                   \
   } while (0)
+
+// Programmatic dependent launch (see gemm_tc.cu): kernels launched through launch_pdl may begin while the previous
+// kernel on the stream drains; they call pdl_wait() before touching global memory and pdl_trigger() when their own
+// dependents may be scheduled.  HSIMAE_PDL=0 launches them as ordinary stream-ordered kernels.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class Kernel, class... Args>
+inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  static const bool pdl = !(getenv("HSIMAE_PDL") && atoi(getenv("HSIMAE_PDL")) == 0);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
 
 void count_launch();
 long long launch_count();

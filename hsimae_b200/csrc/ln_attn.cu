@@ -119,6 +119,7 @@ ln_bwd_vec_kernel(LnBwdArgs a) {
   constexpr int D = 32 * VEC;
   __shared__ float sg[8][D];
   __shared__ float sb[8][D];
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e0 = lane * VEC;
   float gam[VEC], dgam[VEC], dbet[VEC];
@@ -175,6 +176,7 @@ ln_bwd_vec_kernel(LnBwdArgs a) {
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { sg[warp][e0 + j] = dgam[j]; sb[warp][e0 + j] = dbet[j]; }
+  pdl_trigger();   // the row loop is done: the next kernel may start its prologue
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     float g = 0.f, b = 0.f;
@@ -191,9 +193,9 @@ int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t stream) {
   int grid = ceil_div(a.M, 16);
   if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
   // dx_in == dx_out (in-place) is fine: every element is read and written by the same thread
-  if (a.D == 256) ln_bwd_vec_kernel<8><<<grid, 256, 0, stream>>>(a);
-  else if (a.D == 128) ln_bwd_vec_kernel<4><<<grid, 256, 0, stream>>>(a);
-  else if (a.D == 64) ln_bwd_vec_kernel<2><<<grid, 256, 0, stream>>>(a);
+  if (a.D == 256) HS_CHECK_CUDA(launch_pdl(ln_bwd_vec_kernel<8>, dim3(grid), dim3(256), 0, stream, a));
+  else if (a.D == 128) HS_CHECK_CUDA(launch_pdl(ln_bwd_vec_kernel<4>, dim3(grid), dim3(256), 0, stream, a));
+  else if (a.D == 64) HS_CHECK_CUDA(launch_pdl(ln_bwd_vec_kernel<2>, dim3(grid), dim3(256), 0, stream, a));
   else ln_bwd_kernel<<<grid, 256, 0, stream>>>(a);
   HS_CHECK_LAUNCH("ln_bwd_kernel");
   return kOk;
