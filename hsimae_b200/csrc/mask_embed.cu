@@ -204,12 +204,26 @@ embed_fwd_fixed_kernel(EmbedArgs a) {
   float* sX = sCube + g.cube;                                  // [K][D]
   int* sBase = reinterpret_cast<int*>(sX + (size_t)K * D);     // [K] cube offset of each kept token
   int* sTok = sBase + K;                                       // [K]
-  for (int i = threadIdx.x; i < PK * D; i += blockDim.x) {
-    const int d = i / PK, j = i - d * PK;
-    sW[(size_t)j * D + d] = a.W[i];
+  // transposed weight tile: independent 128-bit loads, several in flight per thread (PK is a multiple of 4)
+  {
+    const float4* W4 = reinterpret_cast<const float4*>(a.W);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < PK * D / 4; i += blockDim.x) {
+      const float4 w = __ldg(W4 + i);
+      const int d = (4 * i) / PK, j = 4 * i - d * PK;
+      sW[(size_t)j * D + d] = w.x; sW[(size_t)(j + 1) * D + d] = w.y; sW[(size_t)(j + 2) * D + d] = w.z; sW[(size_t)(j + 3) * D + d] = w.w;
+    }
   }
   const int warp = tid >> 5, lane = tid & 31, nwarps = kSlotThreads >> 5;
   const int dq = D / kEmbedCh;                                 // thread t owns channels t, t + dq, t + 2 dq, t + 3 dq
+  // LayerNorm affine of the channels this lane normalises (first 256-channel slab), loaded once
+  float ga[8], ba[8], gb[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane * 8 + j;
+    ga[j] = (a.ln_a && c < D) ? a.gamma_a[c] : 0.f; ba[j] = (a.ln_a && c < D) ? a.beta_a[c] : 0.f;
+    gb[j] = (a.ln_b && c < D) ? a.gamma_b[c] : 0.f; bb[j] = (a.ln_b && c < D) ? a.beta_b[c] : 0.f;
+  }
   const int rounds = (a.N + gridDim.x * kEmbedSlots - 1) / (gridDim.x * kEmbedSlots);
   for (int rd = 0; rd < rounds; ++rd) {
     const int n = (rd * gridDim.x + blockIdx.x) * kEmbedSlots + slot;
@@ -290,13 +304,13 @@ embed_fwd_fixed_kernel(EmbedArgs a) {
           *reinterpret_cast<float4*>(a.x + m * D + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
           if (a.ln_a) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[j], __ldg(a.gamma_a + i + j), __ldg(a.beta_a + i + j));
+            for (int j = 0; j < 8; ++j) o[j] = i < 256 ? fmaf(xh[j], ga[j], ba[j]) : fmaf(xh[j], __ldg(a.gamma_a + i + j), __ldg(a.beta_a + i + j));
             *reinterpret_cast<uint4*>(a.ln_a + m * D + i) =
                 make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
           }
           if (a.ln_b) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[j], __ldg(a.gamma_b + i + j), __ldg(a.beta_b + i + j));
+            for (int j = 0; j < 8; ++j) o[j] = i < 256 ? fmaf(xh[j], gb[j], bb[j]) : fmaf(xh[j], __ldg(a.gamma_b + i + j), __ldg(a.beta_b + i + j));
             *reinterpret_cast<uint4*>(a.ln_b + m * D + i) =
                 make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
           }
