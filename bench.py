@@ -145,9 +145,9 @@ def time_events(fn, iters: int):
 
 def ncu_traffic(cand: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the candidate kernel, from the committed
-    `ncu --set full` capture (profiles/r01d_ncu_full_kernels.json, written by tools/ncu_summary.py from a
+    `ncu --set full` capture (profiles/r01e_ncu_full_kernels.json, written by tools/ncu_summary.py from a
     tools/prof_kernels.py run at the shapes timed here), or None"""
-    path = os.path.join(ROOT, "profiles", "r01d_ncu_full_kernels.json")
+    path = os.path.join(ROOT, "profiles", "r01e_ncu_full_kernels.json")
     want = {"gemm_tc_dgate_kernel": "d(gate)", "gemm_tc_ares_kernel<SwiGLU": "gated up-projection", "gemm_tc_kernel<ResidLN>": "down-projection",
             "gemm_tc_kernel<Bias> qkv": "qkv projection", "wgrad_tc_kernel dW13": "wgrad dW13", "gemm_tc_kernel<Bias> dgrad": "dgrad K=1376"}
     try:
@@ -205,7 +205,7 @@ def dominant_kernel_roofline(batch: int, pk):
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"]}
     roof.update(kernel=name, us_per_launch=r["t"] * 1e6, traffic=ncu_traffic(name), peak_source=pk["src"],
                 algorithmic_bytes=r["bytes"], algorithmic_flops=r["flops"],
-                note="write-only HBM streams on this part peak at ~3.9 TB/s (tools/membw.py, profiles/r01d_membw.txt); "
+                note="write-only HBM streams on this part peak at ~3.9 TB/s (tools/membw.py, profiles/r01e_membw.txt); "
                      "write-heavy epilogues are bounded by that, not by the 6.55 TB/s copy figure",
                 all_kernels={k: {"us": v["t"] * 1e6, "tflops": v["flops"] / v["t"] / 1e12, "gbs": v["bytes"] / v["t"] / 1e9}
                              for k, v in rows.items()})
