@@ -1,0 +1,28 @@
+"""GPU: every tuning switch of DESIGN.md section 4c still gives reference-matching results.  The switches are read once
+per process, so each combination runs one of the model parity tests in a fresh interpreter."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+COMBOS = [
+    {"HSIMAE_SAVE_GATE": "1"},                                   # saved pre-activations instead of the recompute kernel
+    {"HSIMAE_GEMM_PAIR": "0", "HSIMAE_WGRAD_PAIR": "0"},         # no CTA pairs anywhere
+    {"HSIMAE_GEMM_PAIR": "2"},                                   # CTA pairs wherever legal
+    {"HSIMAE_PDL": "0", "HSIMAE_ATTN_SMALL": "0"},               # plain launches, mma attention for short groups
+    {"HSIMAE_GEMM_ARES": "0", "HSIMAE_WGRAD_FUSED_BIAS": "0"},   # streaming kernels only, separate bias-gradient kernel
+    {"HSIMAE_GEMM_ARES_N": "128", "HSIMAE_GEMM_ARES_N_GATE": "256"},
+]
+
+
+@pytest.mark.parametrize("env", COMBOS, ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
+def test_switch_combination_keeps_parity(env):
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "--tb=short", "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_model_gpu.py"), "-k", "reference_configs and (256-16-40 or 128-8-21)"]
+    r = subprocess.run(cmd, cwd=ROOT, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout, r.stdout[-500:]
