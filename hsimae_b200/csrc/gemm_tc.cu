@@ -1,14 +1,17 @@
 // tcgen05 / TMEM / TMA bf16 GEMMs for sm_100a.
 //
-//   gemm_tc   : C[M,N] = A[M,K] * B[N,K]^T with fused epilogues (epilogue.cuh).
-//               Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA
-//               issuer (single elected thread, accumulators double-buffered in
-//               TMEM), warps 2..5 = epilogue (one accumulator row per thread).
-//               Operands are K-major, 128B-swizzled smem tiles of 64 K-elements.
-//   wgrad_tc  : W[Nout,Kin] += Y^T X, reduction over the token dimension, both
-//               operands MN-major (the reduction index is the slow one in
-//               memory), split over the reduction across CTAs, fp32 red.add
-//               epilogue straight into the gradient arena.
+//   gemm_tc_kernel       : C[M,N] = A[M,K] * B[N,K]^T with fused epilogues.  Persistent, warp-specialised: warp 0 = TMA
+//                          producer, warp 1 = MMA issuer (one thread chosen by elect.sync, accumulator stages in TMEM),
+//                          warps 2.. = epilogue groups (one accumulator row per thread, output boxes through TMA store).
+//                          Operands are K-major, 128B-swizzled smem tiles of 64 K-elements.
+//   gemm_tc_ares_kernel  : the same for K <= 256 with the A block resident in shared memory.
+//   gemm_tc_dgate_kernel : two contractions per accumulator stage (recomputed gate pre-activations + gate gradient).
+//   wgrad_tc_kernel      : W[Nout,Kin] += Y^T X, reduction over the token dimension, both operands MN-major (the
+//                          reduction index is the slow one in memory), split over the reduction across CTAs, fp32
+//                          red.add epilogue straight into the gradient arena.
+//   Every kernel has a CTA-pair form (P = 2: cluster of two, cta_group::2 MMAs over both shared memories) and is launched
+//   with programmatic stream serialisation (prologue overlaps the previous kernel's drain).  What bounds them on B200 is
+//   written up in DESIGN.md section 3.
 //
 // Reference being replaced: the cuBLAS sgemm calls behind nn.Linear forward /
 // backward at /root/reference/Models.py:195-216, 232, 579, 600.
@@ -262,7 +265,7 @@ struct TmemAcc {
 constexpr int kStageBufBytes = 32 * 128;   // one box
 // staging boxes per epilogue warp: the gate epilogue fills two boxes at once (a|b and gate); the others reuse a
 // single box (the TMA unit has read it long before the next one is assembled), which leaves the shared memory
-// to the operand pipeline -- these GEMMs are bound by bytes in flight from L2/HBM, not by the epilogue.
+// to the operand pipeline.
 // The residual / LayerNorm epilogue of the two-stage (256-column) kernel rotates three boxes per warp: each is filled
 // with a residual tile by TMA, updated in place and handed back to TMA as the output tile.
 constexpr int kResidBoxes = 3;
@@ -599,17 +602,15 @@ constexpr int kSmemBudget = 200 * 1024;
 // ---------------------------------------------------------------------------
 // forward / dgrad kernel
 //
-// These GEMMs are short in K (64..1376) and wide in output bytes, so the tile time
-// is set by the epilogue (global loads/stores + element-wise math), not by the
-// MMA.  The accumulator is therefore split into S TMEM stages (512/S columns
-// each) and every stage has its OWN group of four epilogue warps: up to S tiles
-// are being drained concurrently (S warps per scheduler hide each other's
-// TMEM / global latency) while the MMA warp fills the next free stage.
+// These GEMMs are short in K (64..1376) and wide in output bytes: the epilogue (element-wise math, TMEM round trips,
+// output boxes) takes as long as the MMAs of a tile or longer.  The accumulator is therefore split into S TMEM stages
+// (512/S columns each) and every stage has its OWN group of four epilogue warps: up to S tiles are being drained
+// concurrently while the MMA thread fills the next free stage.
 // ---------------------------------------------------------------------------
 // P = 2: CTA-pair mode.  The two CTAs of a cluster own consecutive 128-row blocks; each loads its own A rows and HALF
 // of the weight tile, the leader (cluster rank 0) issues 256-row cta_group::2 MMAs that read both shared memories and
-// write 128 accumulator rows into each CTA's TMEM.  Weight bytes fetched from L2 per output row are halved -- these
-// kernels run at the L2 slice throughput cap (~12 TB/s of SM<->L2 sectors), not at the HBM or tensor roofline.
+// write 128 accumulator rows into each CTA's TMEM.  Weight bytes entering each SM per output row are halved: a streaming
+// kernel is limited by SM ingress (~45 B/clk/SM), 48 KB per 64-deep k-block of a 128x256 tile vs 32 KB in a pair.
 // Barrier ownership: `full` lives in the leader (both producers' TMA bytes land on it), `empty` / `tfull` are
 // signalled in both CTAs by multicast tcgen05.commit, `tempty` lives in the leader (both CTAs' epilogues arrive).
 template <int EPI, int S, int P>
