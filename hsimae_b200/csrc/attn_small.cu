@@ -11,6 +11,11 @@ namespace hsimae {
 namespace {
 
 constexpr int kSmallThreads = 128;
+// CTAs per SM (shared-memory and register budget).  Measured, B200, batch 4096 (fwd / bwd us):
+//   2 tokens: 6 / 4 CTAs 34 / 79,  4 / 3 CTAs 37.5 / 90.5
+//   3 tokens: 4 / 3 CTAs 37.5 / 96 (a 164-byte spill in backward), unconstrained registers 45 / 105, 6 / 4 CTAs 44.5 / 122
+constexpr int small_fwd_per_sm(int len) { return len <= 2 ? 6 : 4; }
+constexpr int small_bwd_per_sm(int len) { return len <= 2 ? 4 : 3; }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -48,7 +53,7 @@ __device__ __forceinline__ float dot(const float (&a)[HD], const float (&b)[HD])
 // forward: out = softmax(q k^T / sqrt(hd)) v, lse in log2 units of the scaled scores (same convention as attn_mma.cu)
 // ---------------------------------------------------------------------------
 template <int HD, int LEN>
-__global__ void __launch_bounds__(kSmallThreads)
+__global__ void __launch_bounds__(kSmallThreads, small_fwd_per_sm(LEN))
 attn_small_fwd_kernel(AttnArgs a, int spc) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_wait();
@@ -126,7 +131,7 @@ attn_small_fwd_kernel(AttnArgs a, int spc) {
 //            dQ_i = sum_j dS_ij K_j;  dK_j = sum_i dS_ij Q_i;  dV_j = sum_i P_ij dO_i
 // ---------------------------------------------------------------------------
 template <int HD, int LEN>
-__global__ void __launch_bounds__(kSmallThreads)
+__global__ void __launch_bounds__(kSmallThreads, small_bwd_per_sm(LEN))
 attn_small_bwd_kernel(AttnArgs a, int spc) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_wait();
@@ -221,15 +226,15 @@ attn_small_bwd_kernel(AttnArgs a, int spc) {
 template <int HD, int LEN>
 int small_fwd(const AttnArgs& a, cudaStream_t stream) {
   const size_t per_sample = (size_t)a.s.K * (3 * a.D * 2 + 16) + (size_t)a.s.K * a.heads * 4;
-  int spc = (int)((54 * 1024) / per_sample);   // four CTAs per SM
+  int spc = (int)(((216 / small_fwd_per_sm(LEN)) * 1024) / per_sample);
   if (spc < 1) spc = 1;
-  const int want = ceil_div(a.N, 8 * kNumSMs);
+  const int want = ceil_div(a.N, 2 * small_fwd_per_sm(LEN) * kNumSMs);
   if (spc > want) spc = want < 1 ? 1 : want;
   const size_t smem = per_sample * spc;
   HS_REQUIRE(smem <= 227 * 1024, "attention(small): %zu bytes of shared memory needed", smem);
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<HD, LEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
-  if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+  if (grid > 2 * small_fwd_per_sm(LEN) * kNumSMs) grid = 2 * small_fwd_per_sm(LEN) * kNumSMs;
   HS_CHECK_CUDA(launch_pdl(attn_small_fwd_kernel<HD, LEN>, dim3(grid), dim3(kSmallThreads), smem, stream, a, spc));
   HS_CHECK_LAUNCH("attn_small_fwd_kernel");
   return kOk;
@@ -238,15 +243,15 @@ int small_fwd(const AttnArgs& a, cudaStream_t stream) {
 template <int HD, int LEN>
 int small_bwd(const AttnArgs& a, cudaStream_t stream) {
   const size_t per_sample = (size_t)a.s.K * ((3 * a.D * 2 + 16) + (2 * a.D * 2 + 16)) + (size_t)a.s.K * a.heads * 4;
-  int spc = (int)((72 * 1024) / per_sample);   // three CTAs per SM
+  int spc = (int)(((216 / small_bwd_per_sm(LEN)) * 1024) / per_sample);
   if (spc < 1) spc = 1;
-  const int want = ceil_div(a.N, 6 * kNumSMs);
+  const int want = ceil_div(a.N, 2 * small_bwd_per_sm(LEN) * kNumSMs);
   if (spc > want) spc = want < 1 ? 1 : want;
   const size_t smem = per_sample * spc;
   HS_REQUIRE(smem <= 227 * 1024, "attention(small) bwd: %zu bytes of shared memory needed", smem);
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<HD, LEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
-  if (grid > 6 * kNumSMs) grid = 6 * kNumSMs;
+  if (grid > 2 * small_bwd_per_sm(LEN) * kNumSMs) grid = 2 * small_bwd_per_sm(LEN) * kNumSMs;
   HS_CHECK_CUDA(launch_pdl(attn_small_bwd_kernel<HD, LEN>, dim3(grid), dim3(kSmallThreads), smem, stream, a, spc));
   HS_CHECK_LAUNCH("attn_small_bwd_kernel");
   return kOk;

@@ -12,7 +12,7 @@ def t(fn, it=20):
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / it * 1e3
 bf = lambda *s: torch.randn(*s, device="cuda").to(torch.bfloat16)
 res = []
-for name, D, H, K, spec in [("spatial", 256, 16, 18, (2, 9, 9, 1)), ("spectral", 256, 16, 18, (9, 2, 1, 9)), ("fusion", 256, 16, 18, (1, 18, 18, 1)),
+for name, D, H, K, spec in [("spatial", 256, 16, 18, (2, 9, 9, 1)), ("spectral", 256, 16, 18, (9, 2, 1, 9)), ("spectral len3", 256, 16, 18, (6, 3, 1, 6)), ("spatial len6", 256, 16, 18, (3, 6, 6, 1)), ("fusion", 256, 16, 18, (1, 18, 18, 1)),
                             ("decoder", 64, 8, 36, (1, 36, 36, 1))]:
     qkv, do = bf(B * K, 3 * D), bf(B * K, D)
     out, lse = ops.attention_forward(qkv, B, D, H, K, *spec)
