@@ -133,6 +133,7 @@ class _Runtime:
         self.device = None
         self.wb = self.wf = self.table = None
         self.sig = None
+        self.checked_ptrs = None
         self.ptr_array = (C.c_void_p * self.n_params)()
 
     def __del__(self):
@@ -153,13 +154,15 @@ class _Runtime:
         self.device = device
         self.sig = None
 
-    def pack(self, params: List[torch.Tensor]):
+    def pack(self, params: List[torch.Tensor], ptrs=None):
         """Refresh the packed bf16 / fp32 operand arenas if any parameter changed."""
-        sig = tuple((p.data_ptr(), p._version) for p in params)
+        if ptrs is None:
+            ptrs = [p.data_ptr() for p in params]
+        sig = (ptrs, [p._version for p in params])
         if sig == self.sig:
             return
-        for i, p in enumerate(params):
-            self.ptr_array[i] = p.data_ptr()
+        if self.sig is None or ptrs != self.sig[0]:
+            self.ptr_array[:] = ptrs
         _lib.check(self.lib.hsimae_pack_params(self.plan, self.ptr_array, _ptr(self.wb), _ptr(self.wf), _ptr(self.table),
                                                _stream()), "pack_params")
         self.sig = sig
@@ -347,7 +350,7 @@ class _HsiBase(nn.Module):
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        for k in ("_rt", "_dp", "_last"):
+        for k in ("_rt", "_rt_accessors", "_dp", "_last"):
             st.pop(k, None)
         return st
 
@@ -383,8 +386,20 @@ class _HsiBase(nn.Module):
         return rt
 
     def _plan_params(self, rt: _Runtime) -> List[torch.Tensor]:
-        named = dict(self.named_parameters())
-        return [named[n] for n in rt.names]
+        """The parameters in the plan's order.  Walking `named_parameters()` costs ~0.6 ms per call for the 535 tensors
+        of HSIMAE-Large (exposed GPU idle time when the training loop synchronises every step, as the reference's
+        does with `loss.item()`), so the owning (sub-module, attribute) pairs are resolved once and each call only
+        re-reads the current Parameter objects from their owners -- replaced parameters, `.to()`, `load_state_dict`
+        are all seen; swapping a whole sub-module for another requires `model._rt_accessors = None`."""
+        acc = self.__dict__.get("_rt_accessors")
+        if acc is None:
+            owners = {}
+            for prefix, mod in self.named_modules():
+                for name in mod._parameters:
+                    owners[(prefix + "." if prefix else "") + name] = (mod._parameters, name)
+            acc = [owners[n] for n in rt.names]
+            self.__dict__["_rt_accessors"] = acc
+        return [d[k] for d, k in acc]
 
     def _prepare(self, imgs: torch.Tensor):
         if not imgs.is_cuda:
@@ -393,11 +408,15 @@ class _HsiBase(nn.Module):
         rt = self._runtime()
         params = self._plan_params(rt)
         dev = imgs.device
-        for p in params:
-            if p.device != dev or p.dtype != torch.float32 or not p.is_contiguous():
-                raise RuntimeError("hsimae_b200: parameters must be contiguous fp32 tensors on the input's CUDA device")
+        # device / dtype / layout can only change together with the storage pointer: validate when a pointer moved
+        ptrs = [p.data_ptr() for p in params]
+        if ptrs != rt.checked_ptrs or dev != rt.device:
+            for p in params:
+                if p.device != dev or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("hsimae_b200: parameters must be contiguous fp32 tensors on the input's CUDA device")
+            rt.checked_ptrs = ptrs
         rt.ensure_device(dev)
-        rt.pack(params)
+        rt.pack(params, ptrs)
         return rt, params
 
     def _check_imgs(self, imgs):

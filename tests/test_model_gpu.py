@@ -337,3 +337,92 @@ def test_other_patch_geometry():
     assert abs(loss.item() - out["loss"].item()) <= TOL_LOSS * abs(out["loss"].item())
     assert rel_err(pred, out["pred_img"]) < TOL_ACT
     _check_grads(model, grads)
+
+
+def test_loss_curve_tracks_oracle_training():
+    """The reference's pretraining loop (Model_Pretraining.py:80-106: AdamW lr 5e-3, betas (0.9, 0.95), decay split on
+    'bias'/'norm') run side by side on the CUDA path and on the fp32 CPU oracle, fed the SAME noise every step: the two
+    loss curves must stay within 2e-3 relative of each other over 12 optimiser steps (measured on B200: 2.5e-5; the
+    bound is the single-step loss tolerance, Adam's sign-like early steps amplify rounding noise on near-zero gradients)."""
+    import Models as M
+    g = tiny_geometry()
+    sd = O.make_state(g, seed=3)
+    model = M.HSIMAE(**TINY)
+    model.load_state_dict({**model.state_dict(), **sd})
+    model = model.to(DEV)
+    leaves = {k: v.clone().requires_grad_(k not in O.FROZEN) for k, v in sd.items()}
+    no_decay = ("bias", "norm")
+
+    def groups(named):
+        named = [(n, p) for n, p in named if p.requires_grad]
+        return [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
+                {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    opt_g = torch.optim.AdamW(groups(model.named_parameters()), lr=5e-3, betas=(0.9, 0.95))
+    opt_c = torch.optim.AdamW(groups(leaves.items()), lr=5e-3, betas=(0.9, 0.95))
+    torch.manual_seed(11); random.seed(11)
+    x = torch.randn(96, 1, 32, 9, 9)
+    xg = x.to(DEV)
+    curve_g, curve_c = [], []
+    for _ in range(12):
+        loss, _, _ = model(xg, mask_ratio=0.5)
+        opt_g.zero_grad(); loss.backward(); opt_g.step()
+        aux = model._last
+        out = O.pretrain_forward(leaves, x, g, aux["noise_t"].cpu(), aux["noise_l"].cpu(), aux["lt"], aux["ll"])
+        assert torch.equal(aux["ids_keep"].cpu(), out["ids_keep"])
+        opt_c.zero_grad(); out["loss"].backward(); opt_c.step()
+        curve_g.append(loss.item()); curve_c.append(out["loss"].item())
+    dev = max(abs(a - b) / abs(b) for a, b in zip(curve_g, curve_c))
+    print("loss curves (cuda / oracle):", [f"{a:.4f}/{b:.4f}" for a, b in zip(curve_g, curve_c)], "max rel dev", dev)
+    assert curve_c[-1] < curve_c[0] and curve_g[-1] < curve_g[0]
+    assert dev < 2e-3, (curve_g, curve_c)
+
+
+def test_packed_weights_follow_parameter_updates():
+    """The bf16 operand arenas are a cache of the fp32 masters keyed by (storage pointer, version): every way the
+    reference drivers change weights -- load_state_dict (Model_Finetuning.py:89-96), optimiser steps, .to() -- and
+    replacing a Parameter object must be seen by the next forward."""
+    import Models as M
+    kw = {k: v for k, v in dict(TINY, num_class=5).items() if not k.startswith("decoder") and k != "norm_pix_loss"}
+    g = tiny_geometry(5)
+    torch.manual_seed(5)
+    x = torch.randn(12, 1, 32, 9, 9, device=DEV)
+
+    def fresh(sd):
+        m = M.HSIViT(**kw)
+        m.load_state_dict({**m.state_dict(), **sd})
+        with torch.no_grad():
+            return m.to(DEV).eval()(x)
+    sd_a = O.make_state(g, seed=1, decoder=False, head=True)
+    sd_b = O.make_state(g, seed=2, decoder=False, head=True)
+    vit = M.HSIViT(**kw)
+    vit.load_state_dict({**vit.state_dict(), **sd_a})
+    vit = vit.to(DEV).eval()
+    with torch.no_grad():
+        ya = vit(x)
+        assert torch.equal(ya, vit(x))                                   # cached arenas: same answer
+        vit.load_state_dict({**vit.state_dict(), **{k: v.to(DEV) for k, v in sd_b.items()}})
+        yb = vit(x)
+    assert torch.equal(yb, fresh(sd_b)) and not torch.equal(ya, yb)
+    # in-place update under no_grad (what optimisers do)
+    with torch.no_grad():
+        vit.cls_head.weight.mul_(2.0); vit.cls_head.bias.mul_(2.0)
+        assert torch.allclose(vit(x), 2.0 * yb, rtol=1e-5, atol=1e-6)
+        # a replaced Parameter object
+        vit.cls_head.weight = torch.nn.Parameter(vit.cls_head.weight.detach() * 0.5)
+        vit.cls_head.bias = torch.nn.Parameter(vit.cls_head.bias.detach() * 0.5)
+        assert torch.allclose(vit(x), yb, rtol=1e-5, atol=1e-6)
+        # dtype round trip re-allocates every storage
+        vit = vit.double().float()
+        assert torch.allclose(vit(x), yb, rtol=1e-5, atol=1e-6)
+    # wrong dtype / device are rejected loudly, not silently reinterpreted
+    vit.cls_head.weight = torch.nn.Parameter(vit.cls_head.weight.detach().double())
+    with pytest.raises(RuntimeError):
+        vit(x)
+    # a deep copy owns its own runtime and parameters
+    import copy
+    vit.cls_head.weight = torch.nn.Parameter(vit.cls_head.weight.detach().float())
+    twin = copy.deepcopy(vit)
+    with torch.no_grad():
+        twin.cls_head.weight.mul_(3.0); twin.cls_head.bias.mul_(3.0)
+        assert torch.allclose(twin(x), 3.0 * yb, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(vit(x), yb, rtol=1e-5, atol=1e-6)
