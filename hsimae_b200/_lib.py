@@ -89,6 +89,11 @@ PROTOTYPES = {
                                           c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "hsimae_adamw_tile_elems": (c_i32, []),
     "hsimae_adamw_step": (c_int, [c_void_p, c_i32, c_i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_void_p]),
+    "hsimae_gwpca_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "hsimae_gwpca_moments": (c_int, [c_void_p, c_i32, c_i64, c_i32, c_i32, C.POINTER(c_i32), c_void_p, c_i64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "hsimae_gwpca_project": (c_int, [c_void_p, c_i32, c_i64, c_i32, c_i32, C.POINTER(c_i32), c_i32, c_void_p, c_void_p, c_void_p,
+                                     c_i32, c_void_p, c_i64, c_void_p]),
     "hsimae_gather_patches": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
 }
 

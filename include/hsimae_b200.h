@@ -183,6 +183,27 @@ int32_t hsimae_adamw_tile_elems(void);
 int hsimae_adamw_step(const void* jobs, int32_t njobs, int32_t ntiles, float one_minus_beta1, float beta2, float one_minus_beta2,
                       float eps, float bias_correction2_sqrt, float neg_step_size, void* stream);
 
+/* ---- group-wise PCA preprocessing -------------------------------------------------------------------
+ * Replaces applyGWPCA (/root/reference/Utils/GroupWisePCA.py:20-34; callers Utils/Preprocessing.py:90-91,192-193):
+ * global min-max scaling, contiguous band groups (split_data, :5-17), one sklearn PCA(n_components, whiten) per group.
+ * The device makes the passes over the pixels, the caller solves the b x b symmetric eigenproblems in between:
+ *   hsimae_gwpca_moments: X [n, c] row-major pixels (dtype 0 = float32, 1 = float64), raw (un-normalised) values ->
+ *     mean [c], minmax [2] = (global min, global max), cov [ngroups, 64, 64] = centred covariance of every group's bands
+ *     (divisor n - 1, rows / columns beyond the group's width are zero); all fp64, all on the device.
+ *   hsimae_gwpca_project: out [n, ngroups * k_per_group] fp64, out[r, g * k + i] = sum_j (X[r, off_g + j] - mean[off_g + j]) * W[g * k + i, j]
+ *     with W [ngroups * k, 64] fp64 on the device (component i of group g times the caller's scale: 1 / sqrt(eigenvalue)
+ *     when whitening, 1 / (max - min) otherwise).  flip_u != 0 additionally negates every output column whose entry of
+ *     largest magnitude (first on ties) is negative -- sklearn <= 1.4's svd_flip(u_based_decision=True), the reference's pin.
+ * group_off: HOST array of ngroups + 1 band offsets (groups of 1..64 bands, at most 16 groups, at most 64 output channels).
+ * ws: device scratch of hsimae_gwpca_workspace_bytes(c, ngroups, nout) bytes (need not be zeroed).  Every reduction has a
+ * fixed order: results are deterministic.  Nothing synchronises. */
+int64_t hsimae_gwpca_workspace_bytes(int32_t c, int32_t ngroups, int32_t nout);
+int hsimae_gwpca_moments(const void* X, int32_t dtype, int64_t n, int32_t c, int32_t ngroups, const int32_t* group_off, void* ws,
+                         int64_t ws_bytes, double* mean, double* minmax, double* cov, void* stream);
+int hsimae_gwpca_project(const void* X, int32_t dtype, int64_t n, int32_t c, int32_t ngroups, const int32_t* group_off,
+                         int32_t k_per_group, const double* mean, const double* W, double* out, int32_t flip_u, void* ws,
+                         int64_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
