@@ -2,6 +2,7 @@
 (tests/golden/feed.npz, oracle/make_golden_feed.py), and the host-side order / flip logic of hsimae_b200.feed."""
 import os
 import random
+import sys
 
 import numpy as np
 import pytest
@@ -79,3 +80,30 @@ def test_oracle_matches_live_reference_dataset():
     random.seed(99)
     flips = FO.draw_flips(len(cut))
     assert np.array_equal(FO.get_batch(scenes, cut, np.arange(len(cut)), flips), ref)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_cut_table_matches_live_reference(tmp_path):
+    """`get_data_cut_file` (Utils/Preprocessing.py:82-118) without the PCA step: same int16 cut table, incl. the numpy-RNG
+    row shuffle, the `ratio` cut, the stride switch at scene 14 and the int16 truncation of max / min."""
+    sys.path.insert(0, REFERENCE)
+    try:
+        from Utils.Preprocessing import get_data_cut_file as ref_cut, get_inital_seq
+    finally:
+        sys.path.remove(REFERENCE)
+    from hsimae_b200.feed import get_data_cut_file, initial_seq
+    for length, size, stride in ((9, 9, 3), (10, 9, 3), (11, 9, 3), (12, 9, 3), (31, 9, 3), (27, 9, 1), (28, 9, 1), (32, 32, 1), (217, 9, 3)):
+        assert np.array_equal(initial_seq(length, size, stride), get_inital_seq(length, size, stride))
+    rng = np.random.default_rng(0)
+    paths = []
+    for i, (h, w) in enumerate([(14, 19), (9, 9), (23, 12)] + [(10, 11)] * 12 + [(21, 30)]):    # 16 scenes: the last two take the stride-1 branch
+        p = tmp_path / f"s{i}.npy"
+        np.save(p, rng.normal(size=(h, w, 32)) * 3.0 + 1.5)
+        paths.append(str(p))
+    for norm, ratio in ((False, 1.0), (True, 0.6)):
+        np.random.seed(7)
+        ref = ref_cut(paths, patch_size=9, norm=norm, GWPCA=False, ratio=ratio)
+        np.random.seed(7)
+        ours = get_data_cut_file(paths, patch_size=9, norm=norm, GWPCA=False, ratio=ratio)
+        assert ours[1].dtype == np.int16 and np.array_equal(ours[1], ref[1])
+        assert all(np.array_equal(a, b) for a, b in zip(ours[0], ref[0]))

@@ -91,3 +91,39 @@ def test_feeds_the_model():
         loss.backward()
         losses.append(float(loss))
     assert len(losses) == (len(cut) + 31) // 32 and all(np.isfinite(losses))
+
+
+def test_raw_scene_to_batches_pipeline(tmp_path):
+    """raw .npy scenes -> device group-wise PCA -> cut table -> device batches (Utils/Preprocessing.py:82-118 +
+    Model_Pretraining.py:40-51,76), against the oracles of each stage."""
+    from hsimae_b200.feed import PatchFeed, get_data_cut_file, split_info
+    from hsimae_b200.gwpca import _auto_sign
+    from oracle import feed_oracle as FO, gwpca_oracle as G
+    rng = np.random.default_rng(3)
+    paths, raw = [], []
+    for i, (h, w) in enumerate(((20, 26), (15, 13))):
+        x = rng.normal(size=(h, w, 6)) @ (rng.normal(size=(6, 120)) * np.linspace(3, 0.5, 6)[:, None])
+        x = np.round((x + 0.2 * rng.normal(size=(h, w, 120))) * 400.0 + 6000.0)
+        np.save(tmp_path / f"s{i}.npy", x)
+        paths.append(str(tmp_path / f"s{i}.npy")); raw.append(x)
+    np.random.seed(11)
+    cubes, cut = get_data_cut_file(paths, patch_size=9, norm=False, GWPCA=True, ratio=0.75)
+    # stage oracles: PCA per scene, then the cut table with the same numpy-RNG shuffles
+    ref_cubes = [G.apply_gwpca(x, 32, 4, True, _auto_sign()) for x in raw]
+    np.random.seed(11)
+    ref_cut = []
+    for k, rc in enumerate(ref_cubes):
+        rows = np.array(split_info(rc.shape, (9, 9, 32), (3, 3, 1), k, 1, 0))
+        np.random.shuffle(rows)
+        ref_cut += list(rows[:int(rows.shape[0] * 0.75)])
+    ref_cut = np.array(ref_cut, dtype=np.int16)
+    assert cut.dtype == np.int16 and np.array_equal(cut, ref_cut)
+    for c, rc in zip(cubes, ref_cubes):
+        assert c.is_cuda and c.dtype == torch.float64 and np.abs(c.cpu().numpy() - rc).max() <= 1e-6 * np.abs(rc).max()
+    feed = PatchFeed([cubes, cut], train=True)
+    idx = list(range(len(cut)))[::-1]
+    random.seed(5)
+    got = feed.batch(idx)
+    random.seed(5)
+    want = FO.get_batch(ref_cubes, ref_cut, idx, FO.draw_flips(len(idx)))
+    assert got.shape == want.shape and np.abs(got.cpu().numpy() - want).max() <= 1e-5     # fp32 cubes of O(1) whitened values
