@@ -148,9 +148,10 @@ class PatchFeed:
         fl_d = flips.to(self.device, dtype=torch.uint8, non_blocking=True).contiguous() if flips is not None else None
         L = _lib.load()
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(L.hsimae_gather_patches(self.scenes.data_ptr(), self.scene_off.data_ptr(), self.scene_hw.data_ptr(), self.bands, self.img,
-                                           self.cut_info.data_ptr(), idx_d.data_ptr(), fl_d.data_ptr() if fl_d is not None else None,
-                                           n, out.data_ptr(), st), "gather_patches")
+        with torch.cuda.device(self.device):        # the launch goes to the current device's context
+            _lib.check(L.hsimae_gather_patches(self.scenes.data_ptr(), self.scene_off.data_ptr(), self.scene_hw.data_ptr(), self.bands,
+                                               self.img, self.cut_info.data_ptr(), idx_d.data_ptr(),
+                                               fl_d.data_ptr() if fl_d is not None else None, n, out.data_ptr(), st), "gather_patches")
         return out
 
     def epoch(self, batch_size: int, shuffle: bool = True):

@@ -72,8 +72,9 @@ def applyGWPCA(X, nc: int = 32, group: int = 4, whiten: bool = True, sign: str =
     mean = torch.empty(c, dtype=torch.float64, device=dev)
     minmax = torch.empty(2, dtype=torch.float64, device=dev)
     cov = torch.empty(ng, 64, 64, dtype=torch.float64, device=dev)
-    _lib.check(L.hsimae_gwpca_moments(x.data_ptr(), dt, n, c, ng, off, ws.data_ptr(), ws.numel(), mean.data_ptr(), minmax.data_ptr(),
-                                      cov.data_ptr(), st), "gwpca_moments")
+    with torch.cuda.device(dev):                    # the launches go to the current device's context
+        _lib.check(L.hsimae_gwpca_moments(x.data_ptr(), dt, n, c, ng, off, ws.data_ptr(), ws.numel(), mean.data_ptr(), minmax.data_ptr(),
+                                          cov.data_ptr(), st), "gwpca_moments")
     cov_h, (lo, hi) = cov.cpu().numpy(), minmax.cpu().tolist()
     rng = hi - lo
     if not rng > 0:
@@ -92,6 +93,7 @@ def applyGWPCA(X, nc: int = 32, group: int = 4, whiten: bool = True, sign: str =
         Wm[g * k:(g + 1) * k, :b] = comps * scale[:, None]
     W = torch.from_numpy(Wm).to(dev)
     out = torch.empty(n, nout, dtype=torch.float64, device=dev)
-    _lib.check(L.hsimae_gwpca_project(x.data_ptr(), dt, n, c, ng, off, k, mean.data_ptr(), W.data_ptr(), out.data_ptr(),
-                                      int(sign == "u"), ws.data_ptr(), ws.numel(), st), "gwpca_project")
+    with torch.cuda.device(dev):
+        _lib.check(L.hsimae_gwpca_project(x.data_ptr(), dt, n, c, ng, off, k, mean.data_ptr(), W.data_ptr(), out.data_ptr(),
+                                          int(sign == "u"), ws.data_ptr(), ws.numel(), st), "gwpca_project")
     return out.view(h, w, nout)

@@ -110,6 +110,9 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_PROCESS_DEVICE = None   # the library configures its kernels (shared-memory limits, TMA descriptors) once per process
+
+
 class _Runtime:
     """Per-model handle on the native plan plus the device arenas it packs into."""
 
@@ -147,6 +150,12 @@ class _Runtime:
     def ensure_device(self, device: torch.device):
         if self.device == device:
             return
+        global _PROCESS_DEVICE
+        if _PROCESS_DEVICE is None:
+            _PROCESS_DEVICE = device
+        elif _PROCESS_DEVICE != device:
+            raise RuntimeError(f"hsimae_b200 runs one process per GPU: this process already uses {_PROCESS_DEVICE}, "
+                               f"got a model on {device} (launch one rank per device, e.g. with torchrun)")
         L = self.lib
         self.wb = torch.zeros(L.hsimae_plan_bf16_arena_elems(self.plan), dtype=torch.bfloat16, device=device)
         self.wf = torch.zeros(L.hsimae_plan_f32_arena_elems(self.plan), dtype=torch.float32, device=device)
@@ -408,6 +417,9 @@ class _HsiBase(nn.Module):
         rt = self._runtime()
         params = self._plan_params(rt)
         dev = imgs.device
+        if dev.index != torch.cuda.current_device():
+            raise RuntimeError(f"hsimae_b200: inputs are on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                               "call torch.cuda.set_device(...) first (kernels are launched on the current device's stream)")
         # device / dtype / layout can only change together with the storage pointer: validate when a pointer moved
         ptrs = [p.data_ptr() for p in params]
         if ptrs != rt.checked_ptrs or dev != rt.device:

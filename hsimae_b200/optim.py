@@ -82,8 +82,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 bc1 = 1 - b1 ** t
                 bc2_sqrt = math.sqrt(1 - b2 ** t)
                 st_ptr = C.c_void_p(torch.cuda.current_stream(sub[0].device).cuda_stream)
-                _lib.check(L.hsimae_adamw_step(C.c_void_p(table.data_ptr()), njobs, ntiles, 1 - b1, b2, 1 - b2, eps, bc2_sqrt, -(lr / bc1), st_ptr),
-                           "adamw_step")
+                with torch.cuda.device(sub[0].device):          # the launch goes to the current device's context
+                    _lib.check(L.hsimae_adamw_step(C.c_void_p(table.data_ptr()), njobs, ntiles, 1 - b1, b2, 1 - b2, eps, bc2_sqrt,
+                                                   -(lr / bc1), st_ptr), "adamw_step")
                 for st in states:
                     st["step"] = t
             # the kernel wrote through raw pointers: tell torch (and the model's packed-weight cache, which watches
