@@ -410,6 +410,15 @@ class _HsiBase(nn.Module):
             self.__dict__["_rt_accessors"] = acc
         return [d[k] for d, k in acc]
 
+    def invalidate_weight_cache(self) -> None:
+        """Force the next forward to re-validate and re-pack the parameters.  Needed only after writes torch cannot see:
+        `p.data.<op>_()` (the `.data` alias has its own version counter) or raw-pointer writes from foreign code.
+        `load_state_dict`, optimiser steps, `.to()` and Parameter replacement are detected automatically."""
+        rt = self.__dict__.get("_rt")
+        if rt is not None:
+            rt.sig = rt.checked_ptrs = None
+        self.__dict__["_rt_accessors"] = None
+
     def _prepare(self, imgs: torch.Tensor):
         if not imgs.is_cuda:
             raise RuntimeError("hsimae_b200 runs on a CUDA (sm_100a) device only; there is no CPU path. "

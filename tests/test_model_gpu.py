@@ -414,6 +414,11 @@ def test_packed_weights_follow_parameter_updates():
         # dtype round trip re-allocates every storage
         vit = vit.double().float()
         assert torch.allclose(vit(x), yb, rtol=1e-5, atol=1e-6)
+        # a write through the `.data` alias is invisible to torch's version counter: explicit invalidation
+        vit.cls_head.weight.data.mul_(2.0); vit.cls_head.bias.data.mul_(2.0)
+        vit.invalidate_weight_cache()
+        assert torch.allclose(vit(x), 2.0 * yb, rtol=1e-5, atol=1e-6)
+        vit.cls_head.weight.mul_(0.5); vit.cls_head.bias.mul_(0.5)
     # wrong dtype / device are rejected loudly, not silently reinterpreted
     vit.cls_head.weight = torch.nn.Parameter(vit.cls_head.weight.detach().double())
     with pytest.raises(RuntimeError):
