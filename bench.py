@@ -93,7 +93,7 @@ def cpu_step_fn(batch: int):
         opt.zero_grad()
         out["loss"].backward()
         opt.step()
-        return float(out["loss"])
+        return float(out["loss"].detach())
     return step
 
 

@@ -89,7 +89,7 @@ def test_feeds_the_model():
     for x in feed.epoch(batch_size=32):
         loss, pred, mask = model(x, mask_ratio=0.5)
         loss.backward()
-        losses.append(float(loss))
+        losses.append(loss.item())
     assert len(losses) == (len(cut) + 31) // 32 and all(np.isfinite(losses))
 
 

@@ -70,7 +70,7 @@ def test_training_loop_with_fused_optimizer_and_schedule():
             loss.backward()
             opt.step()
             sched.step(it)
-            losses.append(float(loss))
+            losses.append(loss.item())
         return losses
 
     a, b = run(False), run(True)
