@@ -42,6 +42,25 @@ def test_mask_bit_exact(ops, n, T, L, lt, ll):
     assert torch.equal(k.cpu(), ko) and torch.equal(r.cpu(), ro) and torch.equal(m.cpu(), mo)
 
 
+def test_mask_random_shapes_with_quantised_noise(ops):
+    """randomised sweep (shapes, visible shapes, noise quantised to a few levels => many exact ties): the stable
+    lowest-index-first tie rule must hold everywhere, bit for bit"""
+    import random as pyrandom
+    rng = pyrandom.Random(1234)
+    g = torch.Generator().manual_seed(99)
+    for _ in range(40):
+        T, L, n = rng.randint(2, 8), rng.randint(2, 16), rng.randint(1, 300)
+        lt, ll = rng.randint(1, T), rng.randint(1, L)
+        levels = rng.choice([2, 3, 5, 1000000])
+        nt = torch.floor(torch.rand(n, T, generator=g) * levels) / levels
+        nl = torch.floor(torch.rand(n, L, generator=g) * levels) / levels
+        k, r, m = ops.mask(nt.to(DEV), nl.to(DEV), lt, ll)
+        ko, ro, mo = O.structured_mask(nt, nl, lt, ll)
+        assert torch.equal(k.cpu(), ko) and torch.equal(r.cpu(), ro) and torch.equal(m.cpu(), mo), (T, L, n, lt, ll, levels)
+        assert torch.equal(torch.sort(r.cpu(), 1).values, torch.arange(T * L).expand(n, -1))
+        assert int(m.sum()) == n * (T * L - lt * ll)
+
+
 def test_mask_kat(ops, golden):
     import hashlib
     z = golden("kat_masks.npz")
