@@ -12,7 +12,7 @@ from hsimae_b200.optim import CosineLRScheduler
 from oracle import gwpca_oracle as G, hsimae_oracle as O
 
 
-@settings(max_examples=150, deadline=None)
+@settings(max_examples=150, deadline=None, derandomize=True)
 @given(T=st.integers(2, 8), L=st.integers(2, 16), ratio=st.floats(0.0, 0.95), seed=st.integers(0, 1000))
 def test_visible_shape_properties(T, L, ratio, seed):
     random.seed(seed)
@@ -27,7 +27,7 @@ def test_visible_shape_properties(T, L, ratio, seed):
     assert abs(np.float32(target) - np.float32(lt * ll)) <= best * (1 + 1e-6) + 1e-6
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(c=st.integers(8, 400), group=st.sampled_from([2, 4, 6, 8]))
 def test_band_groups_partition_the_bands(c, group):
     g = gwpca.band_groups(c, group)
@@ -37,7 +37,7 @@ def test_band_groups_partition_the_bands(c, group):
     assert max(w for _, w in g) - min(w for _, w in g) <= group // 2      # halving keeps the widths within one per round
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(length=st.integers(9, 600), stride=st.sampled_from([1, 3, 9]))
 def test_window_origins_cover_the_axis(length, stride):
     seq = feed.initial_seq(length, 9, stride)
@@ -50,7 +50,7 @@ def test_window_origins_cover_the_axis(length, stride):
     assert np.all(np.diff(seq[:-1]) == 9 // stride)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(iters=st.integers(20, 5000), base=st.floats(1e-5, 1e-1))
 def test_cosine_schedule_properties(iters, base):
     p = torch.nn.Parameter(torch.zeros(1))
