@@ -516,6 +516,31 @@ class _HsiBase(nn.Module):
         return loss_o, logits_o
 
 
+class _PatchLayout:
+    """The reference's public layout helpers of the reconstruction models (pure index permutations, any device)."""
+
+    def patchify(self, imgs):
+        """[N,1,bands,H,W] -> [N, T*L, u*p*p]: token order (t, h, w), element order (u, p, q)  (Models.py:461-473)"""
+        N, _, T, H, W = imgs.shape
+        p, u = self.patch_embed.patch_size[0], self.b_pred_patch_size
+        assert H == W and H % p == 0 and T % u == 0
+        h = w = H // p
+        t = T // u
+        x = imgs.reshape(N, t, u, h, p, w, p).permute(0, 1, 3, 5, 2, 4, 6).reshape(N, t * h * w, u * p ** 2)
+        self.patch_info = (N, T, H, W, p, u, t, h, w)
+        return x
+
+    def unpatchify(self, x):
+        """inverse of :meth:`patchify` for the shape recorded by the last patchify / forward call  (Models.py:475-482)"""
+        N, T, H, W, p, u, t, h, w = self.patch_info
+        return x.reshape(N, t, h, w, u, p, p).permute(0, 1, 4, 2, 5, 3, 6).reshape(N, 1, T, H, W)
+
+    def get_dim_patches(self, T, L, mask_ratio):
+        """(len_t, len_l) as 0-dim LongTensors; consumes one `random.sample` draw  (Models.py:484-493)"""
+        lt, ll = choose_visible_shape(T, L, mask_ratio)
+        return torch.tensor(lt), torch.tensor(ll)
+
+
 def _new_saved() -> _Saved:
     s = _Saved()
     for k in _Saved.__slots__:
@@ -526,7 +551,7 @@ def _new_saved() -> _Saved:
 # ---------------------------------------------------------------------------
 # the three public model classes
 # ---------------------------------------------------------------------------
-class HSIMAE(_HsiBase):
+class HSIMAE(_PatchLayout, _HsiBase):
     """Masked autoencoder with separate spatial / spectral encoders (Models.py:309-634)."""
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=1024, depth=24, num_heads=16,
@@ -577,7 +602,7 @@ class HSIMAE(_HsiBase):
         return rt.encoder_latent(n, lt, ll, False, ws), mask, ids_restore, ids_keep
 
 
-class DualViT(_HsiBase):
+class DualViT(_PatchLayout, _HsiBase):
     """Dual-branch fine-tuning model: classification + reconstruction (Models.py:637-993)."""
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=1024, depth=24, s_depth=6, num_heads=16,

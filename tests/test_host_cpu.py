@@ -114,3 +114,24 @@ def test_forward_without_cuda_fails_loudly():
     m = M.HSIMAE(**TINY)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.randn(2, 1, 32, 9, 9), mask_ratio=0.5)
+
+
+def test_patch_layout_helpers_match_oracle():
+    """HSIMAE.patchify / unpatchify / get_dim_patches (Models.py:461-493) are host-side layout / RNG helpers: any device"""
+    import random
+    import Models
+    from conftest import TINY, tiny_geometry
+    from oracle import hsimae_oracle as O
+    m = Models.HSIMAE(**TINY)
+    g = tiny_geometry()
+    x = torch.randn(5, 1, 32, 9, 9)
+    tok = m.patchify(x)
+    assert tok.shape == (5, 36, 72) and torch.equal(tok, O.cube_to_patches(x, g))
+    assert m.patch_info == (5, 32, 9, 9, 3, 8, 4, 3, 3)
+    assert torch.equal(m.unpatchify(tok), x) and torch.equal(m.unpatchify(tok), O.patches_to_cube(tok, g))
+    random.seed(3)
+    lt, ll = m.get_dim_patches(4, 9, 0.5)
+    random.seed(3)
+    assert (int(lt), int(ll)) == O.choose_visible_shape(4, 9, 0.5) and lt.dtype == torch.int64 and lt.dim() == 0
+    d = Models.DualViT(**{**TINY, "num_class": 5})
+    assert torch.equal(d.patchify(x), tok)

@@ -108,3 +108,21 @@ def test_module_init_matches_reference(R, cls, extra):
         assert torch.equal(a, b)
         assert [n for n, p in r.named_parameters() if not p.requires_grad] == [n for n, p in m.named_parameters() if not p.requires_grad]
         m.load_state_dict(r.state_dict())
+
+
+def test_patch_layout_helpers_match_reference(R):
+    """patchify / unpatchify / get_dim_patches of the drop-in classes against the reference's own methods"""
+    import Models
+    torch.manual_seed(0)
+    ref = quiet(R.HSIMAE, **TINY)
+    ours = Models.HSIMAE(**TINY)
+    x = torch.randn(6, 1, 32, 9, 9)
+    a, b = ref.patchify(x), ours.patchify(x)
+    assert torch.equal(a, b) and tuple(ref.patch_info) == tuple(ours.patch_info)
+    assert torch.equal(ref.unpatchify(a), ours.unpatchify(b)) and torch.equal(ours.unpatchify(b), x)
+    for ratio in (0.25, 0.5, 0.75, 0.8, 0.9):
+        for seed in range(4):
+            random.seed(seed); ra = ref.get_dim_patches(4, 9, ratio); sa = random.getstate()
+            random.seed(seed); rb = ours.get_dim_patches(4, 9, ratio); sb = random.getstate()
+            assert (int(ra[0]), int(ra[1])) == (int(rb[0]), int(rb[1])) and sa == sb
+            assert rb[0].dtype == ra[0].dtype and rb[0].dim() == ra[0].dim()
