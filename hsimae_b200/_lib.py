@@ -88,7 +88,8 @@ PROTOTYPES = {
     "hsimae_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32,
                                           c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "hsimae_adamw_tile_elems": (c_i32, []),
-    "hsimae_adamw_step": (c_int, [c_void_p, c_i32, c_i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_void_p]),
+    "hsimae_adamw_step": (c_int, [c_void_p, c_i32, c_i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  c_void_p]),
     "hsimae_gwpca_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
     "hsimae_gwpca_moments": (c_int, [c_void_p, c_i32, c_i64, c_i32, c_i32, C.POINTER(c_i32), c_void_p, c_i64, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
@@ -97,6 +98,7 @@ PROTOTYPES = {
     "hsimae_gather_patches": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
 }
 
+ABI_VERSION = 2   # include/hsimae_b200.h HSIMAE_ABI_VERSION
 _lib = None
 
 
@@ -115,7 +117,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError => header/library mismatch, surface it
         fn.restype = res
         fn.argtypes = args
-    if lib.hsimae_abi_version() != 1:
+    if lib.hsimae_abi_version() != ABI_VERSION:
         raise RuntimeError("hsimae_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

@@ -23,7 +23,7 @@ struct OptJob {          // mirrored by hsimae_b200/optim.py (48 bytes)
   float* m;
   float* v;
   int32_t n;
-  float decay;           // (float)(1 - lr * weight_decay), evaluated in double on the host like torch's Python scalar
+  float reserved;        // (was the baked-in decay: the table now depends on pointers only, the decay is a launch scalar)
   int32_t tile0;
   int32_t pad;
 };
@@ -38,12 +38,11 @@ __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, fl
 }
 
 __global__ void __launch_bounds__(256)
-adamw_kernel(const OptJob* __restrict__ jobs, const int* __restrict__ tile_job, float w1, float b2, float w2, float eps, float bc2_sqrt,
-             float neg_step) {
+adamw_kernel(const OptJob* __restrict__ jobs, const int* __restrict__ tile_job, float decay, float w1, float b2, float w2, float eps,
+             float bc2_sqrt, float neg_step) {
   const OptJob j = jobs[tile_job[blockIdx.x]];
   const int e0 = (blockIdx.x - j.tile0) * kOptTile;
   const int e1 = e0 + kOptTile < j.n ? e0 + kOptTile : j.n;
-  const float decay = j.decay;
   const bool vec = ((reinterpret_cast<uintptr_t>(j.p) | reinterpret_cast<uintptr_t>(j.g) | reinterpret_cast<uintptr_t>(j.m) |
                      reinterpret_cast<uintptr_t>(j.v)) & 15) == 0;
   if (vec) {
@@ -77,14 +76,14 @@ adamw_kernel(const OptJob* __restrict__ jobs, const int* __restrict__ tile_job, 
 
 extern "C" int32_t hsimae_adamw_tile_elems(void) { return hsimae::kOptTile; }
 
-extern "C" int hsimae_adamw_step(const void* jobs, int32_t njobs, int32_t ntiles, float one_minus_beta1, float beta2, float one_minus_beta2,
-                                 float eps, float bias_correction2_sqrt, float neg_step_size, void* stream) {
+extern "C" int hsimae_adamw_step(const void* jobs, int32_t njobs, int32_t ntiles, float decay, float one_minus_beta1, float beta2,
+                                 float one_minus_beta2, float eps, float bias_correction2_sqrt, float neg_step_size, void* stream) {
   using namespace hsimae;
   if (njobs == 0 || ntiles == 0) return kOk;
   HS_REQUIRE(jobs != nullptr && njobs > 0 && ntiles > 0, "adamw: bad job table");
   HS_REQUIRE(bias_correction2_sqrt > 0.f, "adamw: bias correction must be positive (step >= 1)");
   const OptJob* j = static_cast<const OptJob*>(jobs);
-  adamw_kernel<<<ntiles, 256, 0, (cudaStream_t)stream>>>(j, reinterpret_cast<const int*>(j + njobs), one_minus_beta1, beta2,
+  adamw_kernel<<<ntiles, 256, 0, (cudaStream_t)stream>>>(j, reinterpret_cast<const int*>(j + njobs), decay, one_minus_beta1, beta2,
                                                          one_minus_beta2, eps, bias_correction2_sqrt, neg_step_size);
   HS_CHECK_LAUNCH("adamw_kernel");
   return kOk;

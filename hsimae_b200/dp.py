@@ -82,5 +82,9 @@ def attach(model, process_group=None) -> GradSync:
 
 def broadcast_parameters(model, src: int = 0, process_group=None) -> None:
     """make every replica start from rank `src`'s parameters"""
-    for p in model.parameters():
-        dist.broadcast(p.data, src=src, group=process_group)
+    with torch.no_grad():
+        for p in model.parameters():
+            dist.broadcast(p, src=src, group=process_group)   # in place on `p` itself: bumps `_version`
+    # belt and braces: the packed bf16 / fp32 operand arenas are rebuilt on the next forward whatever torch recorded
+    if hasattr(model, "invalidate_weight_cache"):
+        model.invalidate_weight_cache()

@@ -228,7 +228,7 @@ class _Runtime:
 class _Saved:
     """Python-side record of one forward call (kept alive by the autograd node)."""
     __slots__ = ("rt", "imgs_full", "n_full", "ws_full", "drops_full", "pooled", "imgs_m", "n_m", "lt", "ll", "keep32",
-                 "restore32", "ws_enc", "ws_dec", "drops_m", "dp")
+                 "restore32", "ws_enc", "ws_dec", "drops_m", "dp", "consumed")
 
 
 class _HsiFunction(torch.autograd.Function):
@@ -253,6 +253,11 @@ class _HsiFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         s: _Saved = ctx.saved
+        if s.consumed:
+            # the stashed activations were released by the first backward (torch raises here as well)
+            raise RuntimeError("hsimae_b200: trying to backward through the graph a second time: the saved activations of this "
+                               "forward call have been freed (retain_graph / double backward are not supported); "
+                               "sum the losses and call backward once, as Model_Finetuning.py:153-164 does")
         rt: _Runtime = s.rt
         gouts = list(gouts)
         g_loss = gouts.pop(0) if ctx.has_loss else None
@@ -284,6 +289,7 @@ class _HsiFunction(torch.autograd.Function):
             sync.finish()
         # the stashed activations are consumed: release them now (no retain_graph / double backward)
         s.ws_enc = s.ws_dec = s.ws_full = None
+        s.consumed = True
         out = [None, None, None]
         needs = ctx.needs_input_grad[3:]
         for i in range(ctx.n_params):
@@ -359,7 +365,7 @@ class _HsiBase(nn.Module):
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        for k in ("_rt", "_rt_accessors", "_dp", "_last"):
+        for k in ("_rt", "_rt_accessors", "_dp", "_last", "_last_imgs", "_last_stats"):
             st.pop(k, None)
         return st
 
@@ -502,6 +508,7 @@ class _HsiBase(nn.Module):
                    "decoder_forward")
         pe = self.patch_embed
         self.patch_info = (n, pe.bands, pe.img_size[0], pe.img_size[1], pe.patch_size[0], pe.b_patch_size, T, G, G)
+        self.__dict__["_last_imgs"], self.__dict__["_last_stats"] = imgs, None
         aux = dict(ids_keep=ids_keep, ids_restore=ids_restore, mask=mask, keep32=keep32, restore32=restore32, lt=lt, ll=ll,
                    drops=drops, tokens=tokens, noise_t=noise_t, noise_l=noise_l)
         return loss.view(()), pred_img, mask_img, aux, ws_enc, ws_dec
@@ -539,6 +546,33 @@ class _PatchLayout:
         """(len_t, len_l) as 0-dim LongTensors; consumes one `random.sample` draw  (Models.py:484-493)"""
         lt, ll = choose_visible_shape(T, L, mask_ratio)
         return torch.tensor(lt), torch.tensor(ll)
+
+    # `self.mean` / `self.var` of the reference's forward_loss (Models.py:605-610, 951-955): the per-patch mean and the
+    # per-patch STANDARD DEVIATION sqrt(var_unbiased + 1e-6) of the last reconstructed batch, [N, T*L, 1] each.  The fused
+    # loss kernel keeps them in registers; these attributes are evaluated on first access from the batch of the last
+    # forward call (a reference to it is kept, no copy), so the training loop pays nothing for them.
+    def _patch_stats(self):
+        imgs = self.__dict__.get("_last_imgs")
+        if imgs is None or not self.norm_pix_loss:
+            raise AttributeError("mean / var are set by a forward call with norm_pix_loss=True (Models.py:605-610)")
+        cache = self.__dict__.get("_last_stats")
+        if cache is None:
+            info = self.__dict__.get("patch_info")
+            target = self.patchify(imgs)
+            if info is not None:
+                self.patch_info = info
+            mean = target.mean(dim=-1, keepdim=True)
+            std = (target.var(dim=-1, keepdim=True) + 1.0e-6) ** 0.5
+            cache = self.__dict__["_last_stats"] = (mean, std)
+        return cache
+
+    @property
+    def mean(self):
+        return self._patch_stats()[0]
+
+    @property
+    def var(self):
+        return self._patch_stats()[1]
 
 
 def _new_saved() -> _Saved:

@@ -26,8 +26,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tile = None
-        self._table = None
-        self._key = None
+        self._tables = {}     # (group index, step count slot) -> cached device job table; never part of state_dict()
 
     def _state(self, p):
         st = self.state[p]
@@ -35,6 +34,8 @@ class FusedAdamW(torch.optim.Optimizer):
             st["step"] = 0
             st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        elif not isinstance(st["step"], int):
+            st["step"] = int(st["step"])   # torch.optim.AdamW checkpoints keep the count as a 0-dim tensor
         return st
 
     @torch.no_grad()
@@ -53,25 +54,26 @@ class FusedAdamW(torch.optim.Optimizer):
                 if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
                     raise RuntimeError("FusedAdamW needs contiguous fp32 parameters and gradients")
             lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
-            decay = np.float32(1 - lr * wd)
+            decay = float(np.float32(1 - lr * wd))   # the Python scalar torch hands its foreach kernel, rounded once
             # bias correction depends on the per-parameter step count (a parameter that had no gradient for a while
             # lags behind, as in torch): one launch per distinct count -- one in practice
             by_step = {}
             for p in ps:
                 by_step.setdefault(self._state(p)["step"], []).append(p)
-            tables = group.setdefault("_hsimae_tables", {})
+            tables = self._tables
             for t0, sub in by_step.items():
                 states = [self.state[p] for p in sub]
-                key = (float(decay), tuple((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())
-                                           for p, st in zip(sub, states)))
-                slot = (len(sub), sub[0].data_ptr())
+                # the table holds pointers only (the decay is a launch scalar): it survives every learning-rate change
+                key = tuple((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())
+                            for p, st in zip(sub, states))
+                slot = (gi, len(sub), sub[0].data_ptr())
                 cached = tables.get(slot)
                 if cached is None or cached[0] != key:
                     jobs = np.zeros(len(sub), dtype=_JOB)
                     tile_job, tile0 = [], 0
                     for i, (p, st) in enumerate(zip(sub, states)):
                         nt = (p.numel() + self._tile - 1) // self._tile
-                        jobs[i] = (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), decay, tile0, 0)
+                        jobs[i] = (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), 0.0, tile0, 0)
                         tile_job.append(np.full(nt, i, dtype=np.int32))
                         tile0 += nt
                     blob = np.concatenate([jobs.view(np.uint8), np.concatenate(tile_job).view(np.uint8)])
@@ -83,7 +85,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 bc2_sqrt = math.sqrt(1 - b2 ** t)
                 st_ptr = C.c_void_p(torch.cuda.current_stream(sub[0].device).cuda_stream)
                 with torch.cuda.device(sub[0].device):          # the launch goes to the current device's context
-                    _lib.check(L.hsimae_adamw_step(C.c_void_p(table.data_ptr()), njobs, ntiles, 1 - b1, b2, 1 - b2, eps, bc2_sqrt,
+                    _lib.check(L.hsimae_adamw_step(C.c_void_p(table.data_ptr()), njobs, ntiles, decay, 1 - b1, b2, 1 - b2, eps, bc2_sqrt,
                                                    -(lr / bc1), st_ptr), "adamw_step")
                 for st in states:
                     st["step"] = t

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HSIMAE_ABI_VERSION 1
+#define HSIMAE_ABI_VERSION 2
 
 /* Constructor arguments of the reference model classes that shape the compute
  * path (Models.py:312-332, 640-663, 997-1016). */
@@ -174,14 +174,15 @@ int hsimae_gather_patches(const float* scenes, const int64_t* scene_off, const i
 /* ---- fused multi-tensor AdamW ---------------------------------------------------------------------
  * Replaces optimizer.step() of torch.optim.AdamW as the drivers configure it (/root/reference/Model_Pretraining.py:80-86,
  * 102; Model_Finetuning.py:98-104,165): one launch over a device job table
- *   struct { float* p; const float* g; float* m; float* v; int32 n; float decay (= 1 - lr*wd); int32 tile0; int32 pad; } jobs[njobs];
+ *   struct { float* p; const float* g; float* m; float* v; int32 n; float reserved; int32 tile0; int32 pad; } jobs[njobs];
  *   int32 tile_job[ntiles];           tiles of hsimae_adamw_tile_elems() elements, tile0 = first tile of the job
+ * (the table depends on pointers only: it survives learning-rate changes; decay = 1 - lr*wd is a launch scalar)
  * p *= decay; m += (1-beta1)(g-m); v = v*beta2 + (1-beta2) g*g; p += neg_step_size * m / (sqrt(v)/bc2_sqrt + eps)
  * with neg_step_size = -lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t): the operation order of torch's foreach
  * implementation, scalars evaluated in double on the host as torch does. */
 int32_t hsimae_adamw_tile_elems(void);
-int hsimae_adamw_step(const void* jobs, int32_t njobs, int32_t ntiles, float one_minus_beta1, float beta2, float one_minus_beta2,
-                      float eps, float bias_correction2_sqrt, float neg_step_size, void* stream);
+int hsimae_adamw_step(const void* jobs, int32_t njobs, int32_t ntiles, float decay, float one_minus_beta1, float beta2,
+                      float one_minus_beta2, float eps, float bias_correction2_sqrt, float neg_step_size, void* stream);
 
 /* ---- group-wise PCA preprocessing -------------------------------------------------------------------
  * Replaces applyGWPCA (/root/reference/Utils/GroupWisePCA.py:20-34; callers Utils/Preprocessing.py:90-91,192-193):

@@ -11,7 +11,10 @@ if ROOT not in sys.path:
 sys.dont_write_bytecode = True
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the live mount in the build container; on the GPU box the byte-identical copy made by oracle/fetch_ref.py
 REFERENCE = "/root/reference"
+if not os.path.exists(os.path.join(REFERENCE, "Models.py")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Models.py")):
+    REFERENCE = os.path.join(ROOT, "oracle", "_ref")
 
 
 def pytest_configure(config):

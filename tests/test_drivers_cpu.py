@@ -5,7 +5,9 @@ cosine schedule, datasets / loaders, the first batch -- where, without a GPU, th
 (there is no CPU fallback).  With a GPU *and* the reference present the loops run to completion instead.
 
 Test-side shims only: `timm` (absent: our restated CosineLRScheduler), `matplotlib` (absent: mocks),
-`_BaseDataLoaderIter.next` (removed from torch after 1.12).  The driver sources are imported as they are."""
+`_BaseDataLoaderIter.next` (removed from torch after 1.12), ragged `np.array([[...], []])` (an error since numpy 1.24;
+the drivers were written for 1.2x where it made an object array -- Model_Pretraining.py:112).  The driver sources are
+imported as they are."""
 import os
 import sys
 import types
@@ -20,7 +22,25 @@ from conftest import REFERENCE, ROOT
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE, "Model_Pretraining.py")), reason="reference not mounted")
 
 
-def _import_driver(name):
+class _NumpyCompat:
+    """the driver's `np`: numpy, except that a ragged `np.array(...)` builds an object array as numpy < 1.24 did"""
+
+    def __init__(self, real):
+        self._real = real
+
+    def __getattr__(self, k):
+        return getattr(self._real, k)
+
+    def array(self, obj, *a, **k):
+        try:
+            return self._real.array(obj, *a, **k)
+        except ValueError:
+            return self._real.array(obj, *a, dtype=object, **k)
+
+
+def _import_driver(name, reference_models=False):
+    """import the reference's driver module `name` unchanged; its `from Models import ...` resolves to this repository's
+    drop-in (default) or, with reference_models=True, to the reference's own Models.py (the fp32 baseline run)"""
     from hsimae_b200.optim import CosineLRScheduler
     timm, sched = types.ModuleType("timm"), types.ModuleType("timm.scheduler")
     sched.CosineLRScheduler = CosineLRScheduler
@@ -30,6 +50,9 @@ def _import_driver(name):
     import Models                                   # this repository's drop-in (ROOT is first on sys.path, see conftest)
     assert os.path.dirname(os.path.abspath(Models.__file__)) == ROOT
     sys.modules.pop(name, None)
+    if reference_models:
+        from oracle import fetch_ref
+        shims["Models"] = fetch_ref.import_models()
     with mock.patch.dict(sys.modules, shims):
         sys.path.insert(1, REFERENCE)               # behind ROOT: `from Models import ...` resolves to ours
         try:
@@ -39,6 +62,7 @@ def _import_driver(name):
     sys.modules.pop(name, None)
     mod.CosineLRScheduler = CosineLRScheduler
     mod.tqdm = lambda it, *a, **k: it
+    mod.np = _NumpyCompat(np)
     return mod
 
 

@@ -75,7 +75,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     L = _lib.load()
-    assert L.hsimae_abi_version() == 1
+    assert L.hsimae_abi_version() == 2
 
 
 def test_plan_layout_is_consistent_with_module():
@@ -135,3 +135,29 @@ def test_patch_layout_helpers_match_oracle():
     assert (int(lt), int(ll)) == O.choose_visible_shape(4, 9, 0.5) and lt.dtype == torch.int64 and lt.dim() == 0
     d = Models.DualViT(**{**TINY, "num_class": 5})
     assert torch.equal(d.patchify(x), tok)
+
+
+def test_mean_var_attributes_follow_the_reference_definition():
+    """`self.mean` / `self.var` (Models.py:605-610): per-patch mean and sqrt(unbiased var + 1e-6) of the last batch,
+    evaluated lazily from the batch the last forward call saw (the fused loss kernel keeps them in registers)."""
+    import Models
+    m = Models.HSIMAE(**TINY)
+    with pytest.raises(AttributeError):
+        m.mean
+    x = torch.randn(3, 1, 32, 9, 9)
+    m.__dict__["_last_imgs"], m.__dict__["_last_stats"] = x, None     # what _masked_pass records
+    t = m.patchify(x)
+    assert torch.equal(m.mean, t.mean(dim=-1, keepdim=True)) and m.mean.shape == (3, 36, 1)
+    assert torch.equal(m.var, (t.var(dim=-1, keepdim=True) + 1.0e-6) ** 0.5)
+
+
+def test_second_backward_raises_instead_of_returning_zeros():
+    """a second backward through one forward call must raise like torch does (the stash is released)."""
+    from hsimae_b200 import modules as MM
+    s = MM._new_saved()
+    s.consumed = True
+
+    class Ctx:
+        saved = s
+    with pytest.raises(RuntimeError, match="second time"):
+        MM._HsiFunction.backward(Ctx(), None)

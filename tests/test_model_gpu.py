@@ -431,3 +431,32 @@ def test_packed_weights_follow_parameter_updates():
         twin.cls_head.weight.mul_(3.0); twin.cls_head.bias.mul_(3.0)
         assert torch.allclose(twin(x), 3.0 * yb, rtol=1e-5, atol=1e-6)
         assert torch.allclose(vit(x), yb, rtol=1e-5, atol=1e-6)
+
+
+def test_headline_config_matches_oracle_at_full_size():
+    """BASELINE config-2 itself -- HSIMAE-Large, N = 4096, mask 0.5 -- against the CPU fp32 oracle on the same weights,
+    batch and noise (one oracle step at this size is seconds of host time): loss, the pixel reconstruction and six
+    named gradient tensors spanning the path (decoder head, decoder, fusion, spectral, spatial, patch embedding)."""
+    import Models as M
+    kw = dict(img_size=9, patch_size=3, in_chans=1, bands=32, b_patch_size=8, embed_dim=256, depth=12, num_heads=16, s_depth=9,
+              decoder_embed_dim=64, decoder_depth=8, decoder_num_heads=8, norm_pix_loss=True, trunc_init=True)
+    g = O.Geometry(embed_dim=256, num_heads=16)
+    sd = O.make_state(g, seed=4096, randomize_affine=True)
+    model = M.HSIMAE(**kw)
+    model.load_state_dict({**model.state_dict(), **sd})
+    model = model.to(DEV)
+    torch.manual_seed(7); random.seed(7)
+    x = torch.randn(4096, 1, 32, 9, 9, device=DEV)
+    loss, pred, mask = model(x, mask_ratio=0.5)
+    loss.backward()
+    aux = model._last
+    torch.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
+    out, grads = O.pretrain_step_grads(sd, x.cpu(), g, aux["noise_t"].cpu(), aux["noise_l"].cpu(), aux["lt"], aux["ll"])
+    assert torch.equal(aux["ids_keep"].cpu(), out["ids_keep"]) and torch.equal(mask.cpu(), out["mask_img"])
+    assert abs(loss.item() - out["loss"].item()) <= TOL_LOSS * abs(out["loss"].item())
+    assert rel_err(pred, out["pred_img"]) < TOL_ACT
+    named = dict(model.named_parameters())
+    for k in ("decoder_pred.weight", "decoder_blocks.3.mlp.w2.weight", "blocks.1.attn.proj.weight", "blocks_2.4.mlp.w1.weight",
+              "blocks_1.0.attn.q.weight", "patch_embed.proj.weight"):
+        e = rel_err(named[k].grad, grads[k])
+        assert e < TOL_GRAD, f"{k}: {e:.3g}"
