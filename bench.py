@@ -74,8 +74,44 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
+def reference_available() -> bool:
+    from oracle import fetch_ref
+    return fetch_ref.root() is not None
+
+
+def reference_step_fn(batch: int, device: str):
+    """The UNMODIFIED reference (`HSIMAE` of /root/reference/Models.py, or its byte-identical travelling copy in
+    oracle/_ref) driven exactly as Model_Pretraining.py:68-106 drives it: Large config, AdamW two groups, forward,
+    zero_grad, backward, step, loss.item().  fp32 eager; TF32 off so the arithmetic is the reference's."""
+    from oracle import fetch_ref
+    R = fetch_ref.import_models()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(42); random.seed(42)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = R.HSIMAE(**LARGE).to(device)
+    model.train()
+    no_decay = ("bias", "norm")
+    groups = [{"params": [p for n, p in model.named_parameters() if not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
+              {"params": [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    opt = torch.optim.AdamW(groups, lr=5e-3, weight_decay=5e-2, betas=(0.9, 0.95))
+    x = torch.randn(batch, 1, 32, 9, 9, device=device)
+
+    def step():
+        loss, _, _ = model(x, mask_ratio=0.5)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss.item()
+    return step
+
+
 def cpu_step_fn(batch: int):
-    """the reference algorithm (oracle port) as one training step on the host cores"""
+    """one training step of the reference algorithm on the host cores: the unmodified reference when it is available
+    (kind "reference"), else the oracle port (kind "port")"""
+    if reference_available():
+        return reference_step_fn(batch, "cpu"), "reference"
     from oracle import hsimae_oracle as O
     geo = O.Geometry()
     torch.manual_seed(42); random.seed(42)
@@ -94,13 +130,13 @@ def cpu_step_fn(batch: int):
         out["loss"].backward()
         opt.step()
         return float(out["loss"].detach())
-    return step
+    return step, "port"
 
 
 def run_cpu(steps: int, warmup: int, batch: int = 64, budget_s: float = 1e9):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(batch)
+    step, kind = cpu_step_fn(batch)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter(); done = 0
@@ -109,7 +145,23 @@ def run_cpu(steps: int, warmup: int, batch: int = 64, budget_s: float = 1e9):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return dict(value=batch * done / dt, ms_per_step=1e3 * dt / done, cores=cores, steps=done, batch=batch)
+    return dict(value=batch * done / dt, ms_per_step=1e3 * dt / done, cores=cores, steps=done, batch=batch, kind=kind)
+
+
+def run_gpu_eager(batch: int, steps: int = 5, warmup: int = 3):
+    """the bar SURVEY 2.1 names: the unmodified reference, PyTorch eager fp32, on the SAME B200 and batch"""
+    step = reference_step_fn(batch, "cuda")
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return dict(value=batch / (ms * 1e-3), unit="patches/s", ms_per_step=ms, batch=batch, steps=steps,
+                kind="unmodified reference Models.HSIMAE, PyTorch eager fp32 (TF32 off), torch AdamW, loss.item() every step, cuda:0")
 
 
 def reference_main(args):
@@ -117,12 +169,13 @@ def reference_main(args):
     if rank != 0:
         return
     r = run_cpu(args.steps, max(args.warmup, 1), 64, budget_s=240.0)
-    sample = f"HSIMAE-Large fwd+bwd+AdamW, batch {r['batch']} synthetic patches x {r['steps']} steps, fp32, {r['cores']} torch threads"
+    what = "unmodified reference Models.HSIMAE" if r["kind"] == "reference" else "oracle port"
+    sample = f"{what}: HSIMAE-Large fwd+bwd+AdamW, batch {r['batch']} synthetic patches x {r['steps']} steps, fp32, {r['cores']} torch threads"
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "patches/s", "n_gpus": args.gpus, "steps": r["steps"],
             "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "HSIMAE-Large pretraining step (fwd+bwd+AdamW), mask 0.5, 9x9x32 patches; CPU sample batch 64"},
-            "cpu_baseline": {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
             "e2e": {"value": r["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -306,6 +359,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-PyTorch-eager-on-this-GPU baseline")
     ap.add_argument("--profile", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop (for ncu)")
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "feed", "gwpca"],
                     help="pretrain = the BASELINE.json metric (default); feed / gwpca = the SURVEY 8(f) preprocessing paths, 1 GPU")
@@ -462,9 +516,15 @@ def main():
         line["roofline"] = dominant_kernel_roofline(B, pk)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu(steps=10, warmup=2, batch=64, budget_s=20.0)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port",
-                                "sample": f"same step on the host: batch {r['batch']} x {r['steps']} steps, fp32 oracle port, "
+        what = "unmodified reference Models.HSIMAE" if r["kind"] == "reference" else "oracle port"
+        line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": r["kind"],
+                                "sample": f"same step on the host: batch {r['batch']} x {r['steps']} steps, fp32 {what}, "
                                           f"{r['cores']} torch threads ({r['ms_per_step']:.0f} ms/step)"}
+        if reference_available() and not args.no_gpu_eager:
+            try:
+                line["gpu_eager_baseline"] = run_gpu_eager(B)
+            except Exception as e:   # e.g. out of memory on a smaller part: a reported baseline, never fatal
+                line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
