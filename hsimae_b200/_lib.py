@@ -35,6 +35,19 @@ class GemmDesc(C.Structure):
     ]
 
 
+class MlpDesc(C.Structure):
+    _fields_ = [
+        ("M", c_i32), ("D", c_i32), ("Hp", c_i32),
+        ("X", c_void_p), ("ldx", c_i32), ("W13", c_void_p), ("ldw13", c_i32), ("b13", c_void_p),
+        ("W2", c_void_p), ("ldw2", c_i32), ("b2", c_void_p),
+        ("resid", c_void_p), ("ldr", c_i32), ("resid2", c_void_p),
+        ("rowscale", c_void_p), ("rs_mode", c_i32), ("rs_K", c_i32), ("rs_len_l", c_i32), ("rs_G", c_i32),
+        ("out", c_void_p), ("ldo", c_i32),
+        ("gamma", c_void_p), ("beta", c_void_p), ("ln", c_void_p), ("ldln", c_i32), ("stats", c_void_p),
+        ("g", c_void_p), ("ldg", c_i32),
+    ]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("Mred", c_i32), ("Nout", c_i32), ("Kin", c_i32), ("impl", c_i32),
@@ -83,6 +96,7 @@ PROTOTYPES = {
     "hsimae_head_backward": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsimae_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "hsimae_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
+    "hsimae_mlp_fused": (c_int, [C.POINTER(MlpDesc), c_void_p]),
     "hsimae_attention_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                          c_i32, c_void_p]),
     "hsimae_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32,

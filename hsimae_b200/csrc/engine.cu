@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include "../../include/hsimae_b200.h"
 #include "gemm.cuh"
+#include "block_fused.cuh"
 #include "kernels.cuh"
 
 using namespace hsimae;
@@ -345,7 +346,14 @@ struct Ctx {
   float* grads;
   float* simt;
   cudaStream_t st;
+  bool save = true;   // the pass keeps what backward needs
 };
+
+// HSIMAE_FUSED_MLP=0 restores the two-launch gated MLP (A/B measurements)
+bool fused_mlp_enabled() {
+  static const bool on = !(getenv("HSIMAE_FUSED_MLP") && atoi(getenv("HSIMAE_FUSED_MLP")) == 0);
+  return on;
+}
 
 int run_gemm(const Ctx& c, GemmArgs& a, int epi) {
   a.ln_eps = 1e-5f;
@@ -381,18 +389,25 @@ int block_forward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int Hp
   a.out0 = s.x_mid; a.ld0 = d; a.bias = c.wf + w.bproj; a.resid = x_in; a.ldr = d; a.rs = rs1;
   a.gamma = c.wf + w.g2; a.beta = c.wf + w.be2; a.out1 = s.ln2; a.ld1 = d; a.stats = s.stats2;
   HS_TRY(run_gemm(c, a, kEpiResidLN));
-  // gated MLP up-projection (Models.py:232)
+  // gated MLP (Models.py:232): up-projection, gate, down-projection + residual (+ other branch) + next LayerNorm
+  GemmArgs dn{};
+  dn.M = (int)M; dn.N = d; dn.K = Hp; dn.A = s.g; dn.lda = Hp; dn.B = c.wb + w.w2; dn.ldb = Hp;
+  dn.out0 = s.x_out; dn.ld0 = d; dn.bias = c.wf + w.b2; dn.resid = s.x_mid; dn.ldr = d; dn.resid2 = tail.resid2; dn.rs = rs2;
+  dn.gamma = tail.gamma; dn.beta = tail.beta; dn.out1 = tail.ln; dn.ld1 = d; dn.stats = tail.stats; dn.ln_eps = 1e-5f;
+  if (!c.p->debug_simt && c.p->recompute_gate && fused_mlp_enabled() && mlp_fused_supported(d, Hp)) {
+    // one kernel; the gate output is only written when backward will read it (dW2)
+    MlpFusedArgs m{};
+    m.tail = dn; m.X = s.ln2; m.ldx = d; m.W13 = c.wb + w.w13; m.ldw = d; m.b13 = c.wf + w.b13;
+    m.g = c.save ? s.g : nullptr; m.ldg = Hp;
+    HS_TRY(mlp_fused(m, c.st));
+    return kOk;
+  }
   a = GemmArgs{};
   a.M = (int)M; a.N = 2 * Hp; a.K = d; a.A = s.ln2; a.lda = d; a.B = c.wb + w.w13; a.ldb = d;
   // the pre-activations are only kept for the checker path; the product path recomputes them in backward
   a.out0 = c.p->recompute_gate ? nullptr : s.ab; a.ld0 = 2 * Hp; a.out1 = s.g; a.ld1 = Hp; a.bias = c.wf + w.b13;
   HS_TRY(run_gemm(c, a, kEpiSwiGLU));
-  // down-projection + residual (+ other branch) + next LayerNorm
-  a = GemmArgs{};
-  a.M = (int)M; a.N = d; a.K = Hp; a.A = s.g; a.lda = Hp; a.B = c.wb + w.w2; a.ldb = Hp;
-  a.out0 = s.x_out; a.ld0 = d; a.bias = c.wf + w.b2; a.resid = s.x_mid; a.ldr = d; a.resid2 = tail.resid2; a.rs = rs2;
-  a.gamma = tail.gamma; a.beta = tail.beta; a.out1 = tail.ln; a.ld1 = d; a.stats = tail.stats;
-  HS_TRY(run_gemm(c, a, kEpiResidLN));
+  HS_TRY(run_gemm(c, dn, kEpiResidLN));
   return kOk;
 }
 
@@ -581,7 +596,7 @@ static int encoder_forward_impl(hsimae_plan* p, const void* wb, const void* wf, 
   EncLayout L = enc_layout(p, n, lt, ll, save != 0, ws);
   HS_REQUIRE(ws_bytes >= L.bytes, "encoder workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.bytes);
   if (n == 0) return kOk;
-  Ctx c{p, (const bf16*)wb, (const float*)wf, nullptr, L.simt, (cudaStream_t)stream};
+  Ctx c{p, (const bf16*)wb, (const float*)wf, nullptr, L.simt, (cudaStream_t)stream, save != 0};
   const float* wff = c.wf;
   const int D = p->D;
   ChainSpec ch[3]; enc_chains(p, L, ch);
@@ -753,7 +768,7 @@ int hsimae_decoder_forward(hsimae_plan* p, const void* wb, const void* wf, const
   HS_REQUIRE(ws_bytes >= L.bytes, "decoder workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.bytes);
   HS_REQUIRE(L.P > L.K, "nothing is masked: the reconstruction loss is undefined (Models.py:615 divides by mask.sum())");
   if (n == 0) return kOk;
-  Ctx c{p, (const bf16*)wb, (const float*)wf, nullptr, L.simt, (cudaStream_t)stream};
+  Ctx c{p, (const bf16*)wb, (const float*)wf, nullptr, L.simt, (cudaStream_t)stream, save != 0};
   const float* wff = c.wf;
   const int D = p->D, Dd = p->Dd;
   // decoder_embed (Models.py:579)
@@ -879,6 +894,19 @@ int hsimae_gemm(const hsimae_gemm_desc* d, void* stream) {
   a.ln_eps = 1e-5f;
   if (d->impl == 1) return gemm_simt(a, d->epilogue, d->scratch, (cudaStream_t)stream);
   return gemm_tc(a, d->epilogue, (cudaStream_t)stream);
+}
+
+int hsimae_mlp_fused(const hsimae_mlp_desc* d, void* stream) {
+  HS_REQUIRE(d != nullptr, "null descriptor");
+  MlpFusedArgs m{};
+  GemmArgs& t = m.tail;
+  t.M = d->M; t.N = d->D; t.K = d->Hp; t.B = (const bf16*)d->W2; t.ldb = d->ldw2; t.bias = d->b2;
+  t.out0 = d->out; t.ld0 = d->ldo; t.resid = d->resid; t.ldr = d->ldr; t.resid2 = d->resid2;
+  t.gamma = d->gamma; t.beta = d->beta; t.out1 = d->ln; t.ld1 = d->ldln; t.stats = d->stats; t.ln_eps = 1e-5f;
+  t.rs.scale = d->rowscale; t.rs.mode = d->rs_mode; t.rs.K = d->rs_K > 0 ? d->rs_K : 1; t.rs.len_l = d->rs_len_l > 0 ? d->rs_len_l : 1; t.rs.G = d->rs_G;
+  m.X = (const bf16*)d->X; m.ldx = d->ldx; m.W13 = (const bf16*)d->W13; m.ldw = d->ldw13; m.b13 = d->b13;
+  m.g = (bf16*)d->g; m.ldg = d->ldg;
+  return mlp_fused(m, (cudaStream_t)stream);
 }
 
 int hsimae_wgrad(const hsimae_wgrad_desc* d, void* stream) {

@@ -80,6 +80,34 @@ def gemm(A, B, epilogue, *, impl=IMPL_TC, bias=None, resid=None, resid2=None, ga
     return out
 
 
+def mlp_fused(X, W13, b13, W2, b2, resid, *, gamma=None, beta=None, resid2=None, keep_g=True,
+              rowscale=None, rs_mode=0, rs_K=1, rs_len_l=1, rs_G=1):
+    """out = resid + rs * (W2 (silu(W1 x) * W3 x) + b2) [+ resid2], LayerNorm of the result -- one kernel (csrc/block_fused.cu).
+    W13 / b13 in the library's interleave (pack_interleaved); returns dict(x, ln, stats, g)."""
+    _need_cuda(X, W13, W2, resid)
+    L = _lib.load()
+    M, D = X.shape
+    Hp = W2.shape[1]
+    dev = X.device
+    d = _lib.MlpDesc()
+    d.M, d.D, d.Hp = M, D, Hp
+    d.X, d.ldx, d.W13, d.ldw13, d.b13 = _p(X), X.stride(0), _p(W13), W13.stride(0), _p(b13)
+    d.W2, d.ldw2, d.b2 = _p(W2), W2.stride(0), _p(b2)
+    d.resid, d.ldr, d.resid2 = _p(resid), resid.stride(0), _p(resid2)
+    d.rowscale, d.rs_mode, d.rs_K, d.rs_len_l, d.rs_G = _p(rowscale), rs_mode, rs_K, rs_len_l, rs_G
+    out = {"x": torch.empty(M, D, dtype=torch.float32, device=dev), "ln": None, "stats": None, "g": None}
+    d.out, d.ldo = _p(out["x"]), D
+    if gamma is not None:
+        out["ln"] = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+        out["stats"] = torch.empty(M, 2, dtype=torch.float32, device=dev)
+        d.gamma, d.beta, d.ln, d.ldln, d.stats = _p(gamma), _p(beta), _p(out["ln"]), D, _p(out["stats"])
+    if keep_g:
+        out["g"] = torch.empty(M, Hp, dtype=torch.bfloat16, device=dev)
+        d.g, d.ldg = _p(out["g"]), Hp
+    _lib.check(L.hsimae_mlp_fused(C.byref(d), _stream()), "mlp_fused")
+    return out
+
+
 def wgrad(Y, X, dst0, *, impl=IMPL_TC, dst1=None, row_map=0, rows_valid=None, cols_valid=None, bias0=None, bias1=None):
     """dst[map(n), k] += sum_m Y[m, n] X[m, k]  (accumulates in place)."""
     _need_cuda(Y, X, dst0)

@@ -155,6 +155,27 @@ typedef struct hsimae_wgrad_desc {
 } hsimae_wgrad_desc;
 int hsimae_wgrad(const hsimae_wgrad_desc* d, void* stream);
 
+/* Gated MLP half of a block as ONE kernel (csrc/block_fused.cu; replaces the kEpiSwiGLU + kEpiResidLN pair of launches;
+ * /root/reference/Models.py:231-232 SwiGLU.forward + the residual add of Block.forward :305):
+ *   out = resid + rs * (W2 (silu(W1 x) * (W3 x)) + b2) [+ resid2];  ln = LayerNorm(out) * gamma + beta;  stats = (mean, rstd)
+ * X bf16 [M, D]; W13 bf16 [2 Hp, D] (w1|w3 interleaved by 16 rows, zero rows for the padding), b13 fp32 [2 Hp];
+ * W2 bf16 [D, Hp]; g (optional) receives the bf16 gate output [M, Hp] backward needs.  D in {64,128,192,256}, Hp % 16 == 0. */
+typedef struct hsimae_mlp_desc {
+  int32_t M, D, Hp;
+  const void* X; int32_t ldx;
+  const void* W13; int32_t ldw13;
+  const float* b13;
+  const void* W2; int32_t ldw2;
+  const float* b2;
+  const float* resid; int32_t ldr;
+  const float* resid2;
+  const float* rowscale; int32_t rs_mode, rs_K, rs_len_l, rs_G;
+  float* out; int32_t ldo;
+  const float* gamma; const float* beta; void* ln; int32_t ldln; float* stats;
+  void* g; int32_t ldg;
+} hsimae_mlp_desc;
+int hsimae_mlp_fused(const hsimae_mlp_desc* d, void* stream);
+
 int hsimae_attention_forward(const void* qkv, void* out, float* lse, int32_t n, int32_t D, int32_t heads, int32_t K, int32_t nseq,
                              int32_t len, int32_t seq_step, int32_t tok_step, void* stream);
 int hsimae_attention_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int32_t n,

@@ -284,3 +284,57 @@ def test_attention_fwd_bwd(ops, n, D, heads, lt, ll, kind):
     ref.backward(dout.float())
     dqkv = ops.attention_backward(qkv, out, lse, dout, n, D, heads, K, *spec)
     assert rel_err(dqkv.float(), leaf.grad) < 2e-2   # bf16 O/dO inputs + bf16 output
+
+
+# ---------------------------------------------------------------- fused gated MLP (csrc/block_fused.cu)
+@pytest.mark.parametrize("M,d,H,pair", [(1000, 256, 684, 1), (300, 64, 172, 1), (129, 128, 344, 1), (4099, 256, 684, 1), (77, 64, 172, 1),
+                                        (128, 64, 172, 1), (37000, 256, 684, 1), (40000, 64, 172, 1), (300, 64, 172, 0), (700, 128, 344, 0)])
+@pytest.mark.parametrize("variant", ["ln", "plain", "resid2_rs"])
+def test_mlp_fused(ops, M, d, H, pair, variant, monkeypatch):
+    """One kernel for  x + rs * (w2(silu(w1 h) * w3 h) + b2) [+ resid2]  and the next LayerNorm (Models.py:231-232, 305).
+    Reference: torch fp32 on the same bf16 inputs with the gate output rounded to bf16 where the kernel rounds it
+    (it is the bf16 A operand of the down-projection)."""
+    if pair == 0:
+        pytest.skip("single-CTA form is selected once per process (HSIMAE_FUSED_MLP_PAIR); covered by test_switches_gpu")
+    hp = (H + 15) // 16 * 16
+    h = _rand_bf16(M, d, seed=7)
+    w1, w3 = _rand_bf16(H, d, scale=0.08, seed=8), _rand_bf16(H, d, scale=0.08, seed=9)
+    g = torch.Generator(device=DEV).manual_seed(12)
+    b1, b3 = 0.1 * torch.randn(H, device=DEV, generator=g), 0.1 * torch.randn(H, device=DEV, generator=g)
+    w2 = torch.zeros(d, hp, dtype=torch.bfloat16, device=DEV)
+    w2[:, :H] = _rand_bf16(d, H, scale=0.08, seed=11)
+    b2 = 0.1 * torch.randn(d, device=DEV, generator=g)
+    resid = 3.0 * torch.randn(M, d, device=DEV, generator=g)
+    W13 = ops.pack_interleaved(w1, w3, hp)
+    b13 = ops.pack_interleaved(b1[:, None], b3[:, None], hp)[:, 0].contiguous()
+    gamma = beta = resid2 = rowscale = None
+    kw = {}
+    if variant != "plain":
+        gamma, beta = 1 + 0.1 * torch.randn(d, device=DEV, generator=g), 0.1 * torch.randn(d, device=DEV, generator=g)
+    if variant == "resid2_rs":
+        resid2 = torch.randn(M, d, device=DEV, generator=g)
+        K = 18
+        nb = (M + K - 1) // K
+        rowscale = (torch.rand(nb, device=DEV, generator=g) > 0.3).float() / 0.7
+        kw = dict(rowscale=rowscale, rs_mode=3, rs_K=K, rs_len_l=9, rs_G=1)
+    g_ref = F.silu(h.float() @ w1.float().t() + b1) * (h.float() @ w3.float().t() + b3)
+    y = g_ref.to(torch.bfloat16).float() @ w2[:, :H].float().t() + b2
+    if rowscale is not None:
+        y = y * rowscale[torch.arange(M, device=DEV) // 18][:, None]
+    x_ref = resid + y + (resid2 if resid2 is not None else 0)
+    o = ops.mlp_fused(h, W13, b13, w2, b2, resid, gamma=gamma, beta=beta, resid2=resid2, **kw)
+    assert rel_err(o["g"][:, :H].float(), g_ref) < TOL_BF16
+    if hp > H:
+        assert float(o["g"][:, H:].abs().max()) == 0.0
+    assert rel_err(o["x"], x_ref) < 2e-4          # fp32 stream; the bf16 gate operand bounds the error of the update
+    if gamma is not None:
+        ln_ref = F.layer_norm(x_ref, (d,), gamma, beta, 1e-5)
+        assert rel_err(o["ln"].float(), ln_ref) < TOL_BF16
+        mean, var = x_ref.mean(-1), x_ref.var(-1, unbiased=False)
+        assert rel_err(o["stats"][:, 0], mean) < 1e-3 and rel_err(o["stats"][:, 1], torch.rsqrt(var + 1e-5)) < 1e-3
+    # inference form: no gate output, same stream; and the two-launch path it replaces
+    o2 = ops.mlp_fused(h, W13, b13, w2, b2, resid, gamma=gamma, beta=beta, resid2=resid2, keep_g=False, **kw)
+    assert o2["g"] is None and torch.equal(o2["x"], o["x"])
+    u = ops.gemm(h, W13, ops.EPI_SWIGLU, bias=b13, keep_ab=False)
+    v = ops.gemm(u["g"], w2, ops.EPI_RESID_LN, bias=b2, resid=resid, resid2=resid2, gamma=gamma, beta=beta, **kw)
+    assert rel_err(o["x"], v["x"]) < 2e-5
