@@ -200,17 +200,17 @@ def ncu_traffic(cand: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the candidate kernel, from the committed
     `ncu --set full` capture (profiles/r01e_ncu_full_kernels.json, written by tools/ncu_summary.py from a
     tools/prof_kernels.py run at the shapes timed here), or None"""
-    path = os.path.join(ROOT, "profiles", "r01e_ncu_full_kernels.json")
-    want = {"gemm_tc_dgate_kernel": "d(gate)", "gemm_tc_ares_kernel<SwiGLU": "gated up-projection", "gemm_tc_kernel<ResidLN>": "down-projection",
-            "gemm_tc_kernel<Bias> qkv": "qkv projection", "wgrad_tc_kernel dW13": "wgrad dW13", "gemm_tc_kernel<Bias> dgrad": "dgrad K=1376"}
-    try:
-        rows = json.load(open(path))
-        for key, label in want.items():
-            if cand.startswith(key):
-                hit = [r for r in rows if r["label"].startswith(label)][0]
-                return hit["dram_read_bytes"] + hit["dram_write_bytes"]
-    except Exception:
-        pass
+    want = {"gemm_tc_dgate_kernel": "d(gate)", "mlp_fused_kernel": "fused gated MLP", "gemm_tc_kernel<Bias> qkv": "qkv projection",
+            "wgrad_tc_kernel dW13": "wgrad dW13", "gemm_tc_kernel<Bias> dgrad": "dgrad K=1376"}
+    for name in ("r02_ncu_full_kernels.json", "r01e_ncu_full_kernels.json"):
+        try:
+            rows = json.load(open(os.path.join(ROOT, "profiles", name)))
+            for key, label in want.items():
+                if cand.startswith(key):
+                    hit = [r for r in rows if r["label"].startswith(label)][0]
+                    return hit["dram_read_bytes"] + hit["dram_write_bytes"]
+        except Exception:
+            pass
     return None
 
 
@@ -229,24 +229,27 @@ def dominant_kernel_roofline(batch: int, pk):
     dab = bf(M, 2 * H)
     gw13 = torch.zeros(684, D, device=dev); gw13b = torch.zeros(684, D, device=dev)
     per_step = 21   # encoder blocks per direction
+    x2 = bf(M, D)          # the d(gate) call reads TWO distinct activations (dy and the LayerNorm-2 output)
+    b13, b2 = torch.zeros(2 * H, device=dev), torch.zeros(D, device=dev)
+    # name -> (launch, ALGORITHMIC flops per SURVEY 8(d) accounting, algorithmic bytes, launches per step, EXECUTED flops)
     cands = {
         "gemm_tc_dgate_kernel d(a|b) from [M,256]x{[256,1376],[256,688]}": (
-            lambda: ops.gemm(x, w2t, ops.EPI_DGATE, A2=x, B2=w13), 2 * M * D * 3 * H, 2 * (2 * M * D + 3 * H * D + M * 2 * H), per_step),
-        "gemm_tc_ares_kernel<SwiGLU, g only> [M,256]x[256,1376]": (
-            lambda: ops.gemm(x, w13, ops.EPI_SWIGLU, keep_ab=False), 2 * M * 2 * H * D, 2 * (M * D + 2 * H * D + M * H), per_step),
-        "gemm_tc_kernel<ResidLN> [M,688]x[688,256]": (lambda: ops.gemm(g, w2, ops.EPI_RESID_LN, resid=resid, gamma=gamma, beta=beta),
-                                                      2 * M * D * H, 2 * (M * H + D * H + M * D) + 8 * M * D, per_step),
+            lambda: ops.gemm(x, w2t, ops.EPI_DGATE, A2=x2, B2=w13), 2 * M * D * H, 2 * (2 * M * D + 3 * H * D + M * 2 * H), per_step,
+            2 * M * D * 3 * H),   # + the recomputed up-projection (2 M D 2H), which SURVEY 8(d)'s 1.893 GFLOP/patch does not contain
+        "mlp_fused_kernel [M,256]x[256,1376] -> gate -> x[688,256] + residual + LayerNorm (training: g kept)": (
+            lambda: ops.mlp_fused(x, w13, b13, w2, b2, resid, gamma=gamma, beta=beta), 2 * M * 3 * H * D,
+            2 * M * D + 4 * M * D + 2 * 3 * H * D + 2 * M * H + 4 * M * D + 2 * M * D, per_step, 2 * M * 3 * H * D),
         "gemm_tc_kernel<Bias> qkv [M,256]x[256,768]": (lambda: ops.gemm(x, wqkv, ops.EPI_BIAS_BF16), 2 * M * 3 * D * D,
-                                                            2 * (M * D + 3 * D * D + M * 3 * D), per_step),
+                                                            2 * (M * D + 3 * D * D + M * 3 * D), per_step, 2 * M * 3 * D * D),
         "wgrad_tc_kernel dW13 [1376,M]x[M,256]": (lambda: ops.wgrad(dab, x, gw13, dst1=gw13b, row_map=1, rows_valid=684),
-                                                  2 * M * 2 * H * D, 2 * (M * 2 * H + M * D) + 4 * 2 * 684 * D, per_step),
+                                                  2 * M * 2 * H * D, 2 * (M * 2 * H + M * D) + 4 * 2 * 684 * D, per_step, 2 * M * 2 * H * D),
         "gemm_tc_kernel<Bias> dgrad [M,1376]x[1376,256]": (lambda: ops.gemm(dab, w13.t().contiguous(), ops.EPI_BIAS_BF16),
-                                                           2 * M * 2 * H * D, 2 * (M * 2 * H + 2 * H * D + M * D), per_step),
+                                                           2 * M * 2 * H * D, 2 * (M * 2 * H + 2 * H * D + M * D), per_step, 2 * M * 2 * H * D),
     }
     rows = {}
-    for name, (fn, flops, nbytes, count) in cands.items():
+    for name, (fn, flops, nbytes, count, executed) in cands.items():
         t = time_events(fn, 20)
-        rows[name] = dict(t=t, flops=flops, bytes=nbytes, count=count)
+        rows[name] = dict(t=t, flops=flops, bytes=nbytes, count=count, executed=executed)
     name = max(rows, key=lambda k: rows[k]["t"] * rows[k]["count"])
     r = rows[name]
     t_tensor, t_hbm = r["flops"] / (pk["tf"] * 1e12), r["bytes"] / (pk["hbm"] * 1e9)
@@ -257,13 +260,81 @@ def dominant_kernel_roofline(batch: int, pk):
         ach = r["flops"] / r["t"] / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"]}
     roof.update(kernel=name, us_per_launch=r["t"] * 1e6, traffic=ncu_traffic(name), peak_source=pk["src"],
-                algorithmic_bytes=r["bytes"], algorithmic_flops=r["flops"],
+                algorithmic_bytes=r["bytes"], algorithmic_flops=r["flops"], executed_flops=r["executed"],
+                executed_tflops=r["executed"] / r["t"] / 1e12,
                 note="write-only HBM streams on this part peak at ~3.9 TB/s (tools/membw.py, profiles/r01e_membw.txt); "
                      "write-heavy epilogues are bounded by that, not by the 6.55 TB/s copy figure",
-                all_kernels={k: {"us": v["t"] * 1e6, "tflops": v["flops"] / v["t"] / 1e12, "gbs": v["bytes"] / v["t"] / 1e9}
-                             for k, v in rows.items()})
+                all_kernels={k: {"us": v["t"] * 1e6, "tflops": v["flops"] / v["t"] / 1e12, "executed_tflops": v["executed"] / v["t"] / 1e12,
+                                 "gbs": v["bytes"] / v["t"] / 1e9} for k, v in rows.items()})
     return roof
 
+
+
+# ----------------------------------------------------------------------------- in-step kernel accounting
+GEMM_FLOP_PER_PATCH = 3 * 626.0e6 - 2 * 1.33e6   # algorithmic GEMM FLOP / patch fwd+bwd (no dX for the patch embedding)
+
+
+def step_kernel_accounting(step_fn, batch: int, pk):
+    """One extra (untimed) step under the CUPTI activity profiler: device time of EVERY kernel of the step by name.
+    Gives (c) the GEMM-family fraction the north-star target is about -- algorithmic GEMM + weight-gradient FLOPs of a
+    step / the summed in-step time of the kernels that execute them / peak -- and (d) the HBM-bound kernels with their
+    algorithmic bytes against the measured HBM peak."""
+    from torch.profiler import profile, ProfilerActivity
+    from hsimae_b200 import _lib
+    lib = _lib.load()
+    try:
+        # plain stream order for this step: with programmatic dependent launch the next kernel's prologue starts (and its
+        # activity record opens) while the previous kernel drains, so consecutive durations would overlap
+        was = lib.hsimae_set_pdl(0)
+        try:
+            step_fn()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step_fn()
+                torch.cuda.synchronize()
+        finally:
+            lib.hsimae_set_pdl(was)
+        evs = [e for e in prof.events() if getattr(e, "device_time", 0) and "Memcpy" not in e.name and "Memset" not in e.name]
+    except Exception as e:   # a reported breakdown, never fatal
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    agg = {}
+    for e in evs:
+        a = agg.setdefault(e.name, [0, 0.0])
+        a[0] += 1; a[1] += e.device_time   # us
+    fam = {"gemm": ("gemm_tc", "mlp_fused", "wgrad_tc"), "attention": ("attn_",), "ln_bwd": ("ln_bwd",), "embed": ("embed_",),
+           "loss": ("loss_kernel",), "fill": ("fill_",), "mask": ("mask_kernel",), "pack": ("pack_kernel",), "nccl": ("nccl",)}
+    fams = {k: [0, 0.0] for k in fam}; fams["other (optimizer, rand, casts)"] = [0, 0.0]
+    for name, (n, us) in agg.items():
+        for k, keys in fam.items():
+            if any(x in name for x in keys):
+                fams[k][0] += n; fams[k][1] += us; break
+        else:
+            fams["other (optimizer, rand, casts)"][0] += n; fams["other (optimizer, rand, casts)"][1] += us
+    total = sum(v[1] for v in fams.values())
+    g_us = fams["gemm"][1]
+    out = {"kernel_time_sum_ms": total / 1e3, "launches": sum(v[0] for v in fams.values()),
+           "families": {k: {"launches": v[0], "ms": v[1] / 1e3, "share": v[1] / total} for k, v in fams.items() if v[0]},
+           "note": "one untimed step in plain stream order (programmatic dependent launch off) under the CUPTI activity profiler",
+           "gemm_family_frac": {"algorithmic_tflop_per_step": batch * GEMM_FLOP_PER_PATCH / 1e12, "in_step_ms": g_us / 1e3,
+                                "achieved_tflops": batch * GEMM_FLOP_PER_PATCH / (g_us * 1e-6) / 1e12, "peak_tflops": pk["tf_sus"],
+                                "frac": batch * GEMM_FLOP_PER_PATCH / (g_us * 1e-6) / 1e12 / pk["tf_sus"], "peak": "sustained, " + pk["src"],
+                                "frac_of_burst": batch * GEMM_FLOP_PER_PATCH / (g_us * 1e-6) / 1e12 / pk["tf"],
+                                "note": "GEMM + weight-gradient kernels only (tcgen05): algorithmic FLOPs, recomputation not counted"}}
+    # HBM-bound kernels: algorithmic bytes per launch (every operand / result once; DESIGN.md section 3), Large, mask 0.5
+    B, K, P, D, Dd, PK = batch, 18, 36, 256, 64, 72
+    M, Md = B * K, B * P
+    byts = {"embed_fwd": B * K * PK * 4 + M * D * 4 + 2 * M * D * 2, "embed_bwd": B * K * PK * 4 + 2 * M * D * 4,
+            "loss_kernel": B * CUBE * 4 + Md * 80 * 4 + Md * 80 * 2 + 2 * B * CUBE * 4, "fill_fwd": M * Dd * 4 + Md * Dd * 4 + Md * Dd * 2,
+            "fill_bwd": Md * Dd * 4 + M * Dd * 2, "mask_kernel": B * (13 * 4 + (18 + 36) * 8 + 36 * 4 + 54 * 4),
+            "ln_bwd_vec_kernel<8>": M * D * (2 + 4 + 4 + 4 + 2), "ln_bwd_vec_kernel<2>": Md * Dd * (2 + 4 + 4 + 4 + 2)}
+    mem = {}
+    for name, (n, us) in agg.items():
+        for key, nb in byts.items():
+            if key in name:
+                t = us / n * 1e-6
+                mem[key] = {"launches": n, "us": us / n, "algorithmic_bytes": nb, "gbs": nb / t / 1e9, "frac_of_hbm_peak": nb / t / 1e9 / pk["hbm"]}
+    out["membound_kernels"] = mem
+    out["top_kernels"] = [{"name": k[:90], "launches": v[0], "ms": v[1] / 1e3} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]]
+    return out
 
 # ----------------------------------------------------------------------------- secondary workloads (SURVEY 8f)
 def feed_main(args):
@@ -348,6 +419,187 @@ def gwpca_main(args):
                       "max_rel_err_vs_oracle": err}), flush=True)
 
 
+
+# ----------------------------------------------------------------------------- BASELINE.json configs[3] / configs[4]
+DUAL = dict(img_size=9, patch_size=3, in_chans=1, bands=32, b_patch_size=8, num_class=17, embed_dim=256, depth=12, num_heads=16, s_depth=9,
+            drop_path=0.2, decoder_embed_dim=64, decoder_depth=8, decoder_num_heads=8, norm_pix_loss=True, trunc_init=True)
+VIT = dict(img_size=9, patch_size=3, in_chans=1, bands=32, b_patch_size=8, num_class=17, embed_dim=256, depth=12, num_heads=16, s_depth=9,
+           trunc_init=True)
+FT_FLOP_PER_STEP = 3 * (32 * 1200.3e6 + 103 * 298.3e6)   # unmasked encoder on 32 labelled + masked branch on 103, fwd+bwd
+SCENE_FLOP = 512 * 217 * 1200.3e6                        # encoder-only forward over every pixel-centred window
+
+
+def _events(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        r = fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps, r
+
+
+def finetune_main(args):
+    """`--workload finetune` (BASELINE.json configs[3]): the dual-branch fine-tuning step of Model_Finetuning.py:147-166 --
+    DualViT-Large, 32 labelled + 71 unlabelled Salinas-shaped tiles, mask 0.8, lambda 10, drop_path 0.2, CE(ignore_index=0),
+    AdamW -- device-resident and end to end (x, x_u, y from pinned host memory and the logits read back every step, as the
+    driver does at :150-156); the unmodified reference on the host cores beside it."""
+    import Models
+    from hsimae_b200 import _lib
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0); random.seed(0)
+    model = Models.DualViT(**DUAL).to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-2)
+    crit = torch.nn.CrossEntropyLoss(ignore_index=0)
+    nl, nu = args.labelled, args.unlabelled
+    hx, hxu = torch.randn(nl, 1, 32, 9, 9).pin_memory(), torch.randn(nu, 1, 32, 9, 9).pin_memory()
+    hy = torch.randint(1, 17, (nl,)).pin_memory()
+    x, xu, y = hx.to(dev), hxu.to(dev), hy.to(dev)
+    lib = _lib.load()
+    stepper = None
+    if not args.no_graph:
+        try:
+            from hsimae_b200.graph import GraphedFinetuneStep
+            stepper = GraphedFinetuneStep(model, opt, crit, lamda=10.0, mask_ratio=0.8)
+        except Exception as e:   # the eager step is always available
+            print(f"# CUDA-graph step unavailable: {type(e).__name__}: {e}", file=sys.stderr)
+
+    def step_eager(a, b, c):
+        loss_rec, _, _, logits = model(a, b, mask_ratio=0.8)
+        loss = 10 * loss_rec + crit(logits, c)
+        opt.zero_grad(); loss.backward(); opt.step()
+        return loss, logits
+
+    step = (lambda a, b, c: stepper(a, b, c)) if stepper is not None else step_eager
+    l0 = lib.hsimae_launch_count()
+    ms, _ = _events(lambda: step(x, xu, y), args.steps, max(args.warmup, 3))
+    launches = (lib.hsimae_launch_count() - l0) / (args.steps + max(args.warmup, 3))
+
+    def e2e_step():
+        a, b, c = hx.to(dev, non_blocking=True), hxu.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)
+        loss, logits = step(a, b, c)
+        return logits.detach().cpu()          # Model_Finetuning.py:156
+    e2e_ms, _ = _events(e2e_step, args.steps, 2)
+    pk = peaks()
+    tf = FT_FLOP_PER_STEP / (ms * 1e-3) / 1e12
+    line = {"metric": "dual-branch fine-tuning patches/sec (DualViT-Large, fwd+bwd+AdamW)", "value": (nl + nu) / (ms * 1e-3), "unit": "patches/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"Model_Finetuning.py:147-166 step, {nl} labelled + {nu} unlabelled 9x9x32 tiles, 17 classes, mask 0.8, "
+                                   "lambda 10, drop_path 0.2 (BASELINE.json configs[3])",
+                       "execution": "one CUDA graph per visible shape (hsimae_b200.graph)" if stepper is not None else "eager launches"},
+            "e2e": {"value": (nl + nu) / (e2e_ms * 1e-3), "unit": "patches/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": (nl + nu) * CUBE * 4 + nl * 8, "d2h_bytes_per_step": nl * 17 * 4},
+            "gpu_launches_per_step": launches,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf / pk["tf_sus"], "traffic": None,
+                         "peak_source": "sustained, " + pk["src"],
+                         "note": "whole step (~1000 kernels on 103 samples): launch / latency bound, not a kernel roofline"}}
+    if not args.no_cpu_baseline and reference_available():
+        from oracle import fetch_ref
+        R = fetch_ref.import_models()
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0); random.seed(0)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = R.DualViT(**DUAL).train()
+        ropt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=5e-2)
+        cx, cxu, cy = hx.clone(), hxu.clone(), hy.clone()
+
+        def cpu_step():
+            loss_rec, _, _, logits = ref(cx, cxu, mask_ratio=0.8)
+            loss = 10 * loss_rec + crit(logits, cy)
+            ropt.zero_grad(); loss.backward(); ropt.step()
+        cpu_step()
+        t0 = time.perf_counter(); n = 0
+        while n < 5 and time.perf_counter() - t0 < 20:
+            cpu_step(); n += 1
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": (nl + nu) / dt, "unit": "patches/s", "cores": os.cpu_count(), "kind": "reference",
+                                "sample": f"unmodified reference DualViT, same batch, {n} steps, fp32 ({dt * 1e3:.0f} ms/step)"}
+    print(json.dumps(line), flush=True)
+
+
+def scene_main(args):
+    """`--workload scene` (BASELINE.json configs[4]): dense per-pixel classification of a Salinas-sized synthetic scene
+    (512 x 217 x 32) with HSIViT-Large, 9x9 windows gathered on the device (Model_Finetuning.py:243-301 semantics)."""
+    import Models
+    from hsimae_b200.scene import classify_scene
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    vit = Models.HSIViT(**VIT).to(dev).eval()
+    hscene = torch.randn(512, 217, 32).pin_memory()
+    scene = hscene.to(dev)
+    batch = args.scene_batch
+    ms, _ = _events(lambda: classify_scene(vit, scene, batch=batch), max(args.steps // 4, 3), 2)
+
+    def e2e():
+        out = classify_scene(vit, hscene.to(dev, non_blocking=True), batch=batch)
+        return (out[:, 1:].argmax(1) + 1).to(torch.int16).cpu()     # Model_Finetuning.py:277-280
+    e2e_ms, labels = _events(e2e, max(args.steps // 4, 3), 1)
+    pk = peaks()
+    npx = 512 * 217
+    tf = SCENE_FLOP / (ms * 1e-3) / 1e12
+    line = {"metric": "dense scene classification pixels/sec (HSIViT-Large, 512x217x32, 9x9 windows)", "value": npx / (ms * 1e-3), "unit": "pixels/s",
+            "n_gpus": 1, "steps": max(args.steps // 4, 3), "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"whole-scene inference, on-device sliding windows, batches of {batch} windows (BASELINE.json configs[4])"},
+            "e2e": {"value": npx / (e2e_ms * 1e-3), "unit": "pixels/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": hscene.numel() * 4,
+                    "d2h_bytes_per_step": npx * 2},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf / pk["tf_sus"], "traffic": None,
+                         "peak_source": "sustained, " + pk["src"], "note": "encoder-only forward, 1200.3 MFLOP per window (SURVEY 8d)"}}
+    if not args.no_cpu_baseline and reference_available():
+        from oracle import fetch_ref
+        R = fetch_ref.import_models()
+        torch.set_num_threads(os.cpu_count() or 1)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = R.HSIViT(**VIT).eval()
+        xb = torch.randn(256, 1, 32, 9, 9)
+        with torch.no_grad():
+            ref(xb)
+            t0 = time.perf_counter(); n = 0
+            while n < 8 and time.perf_counter() - t0 < 20:
+                ref(xb); n += 1
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": 256 / dt, "unit": "pixels/s", "cores": os.cpu_count(), "kind": "reference",
+                                "sample": f"unmodified reference HSIViT on host cubes, batch 256 (Model_Finetuning.py:265) x {n}, fp32"}
+    print(json.dumps(line), flush=True)
+
+
+def dp_parity_check(model, rank: int, world: int, dev):
+    """N-rank averaged gradients == 1-rank gradients on the concatenated batch (one shot, before timing): every rank runs
+    the global parity batch alone, then its shard with the NCCL exchange attached; same noise, same visible shape."""
+    import torch.distributed as dist
+    import hsimae_b200.modules as mod
+    from hsimae_b200 import dp
+    per = 16
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x_all = torch.randn(world * per, 1, 32, 9, 9, generator=g).to(dev)
+    nt_all, nl_all = torch.rand(world * per, 4, generator=g).to(dev), torch.rand(world * per, 9, generator=g).to(dev)
+
+    def run(x, nt, nl):
+        feed = [nt.contiguous(), nl.contiguous()]
+        orig_s, orig_r = mod.choose_visible_shape, torch.rand
+        mod.choose_visible_shape = lambda T, L, r: (3, 6); torch.rand = lambda *a, **k: feed.pop(0)
+        try:
+            model.zero_grad(); loss, _, _ = model(x, mask_ratio=0.5)
+        finally:
+            mod.choose_visible_shape, torch.rand = orig_s, orig_r
+        loss.backward()
+        return {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    full = run(x_all, nt_all, nl_all)
+    sync = dp.attach(model)
+    sl = slice(rank * per, (rank + 1) * per)
+    part = run(x_all[sl], nt_all[sl], nl_all[sl])
+    worst = max(float((part[k] - full[k]).norm() / (full[k].norm() + 1e-12)) for k in full if not k.endswith("attn.k.bias"))
+    t = torch.tensor([worst], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    model.zero_grad(set_to_none=True)
+    if t.item() > 5e-3:
+        raise SystemExit(f"data-parallel gradients differ from the single-replica gradients: max rel {t.item():.3e}")
+    return float(t.item()), sync
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -361,8 +613,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-PyTorch-eager-on-this-GPU baseline")
     ap.add_argument("--profile", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop (for ncu)")
-    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "feed", "gwpca"],
-                    help="pretrain = the BASELINE.json metric (default); feed / gwpca = the SURVEY 8(f) preprocessing paths, 1 GPU")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune", "scene", "feed", "gwpca"],
+                    help="pretrain = the BASELINE.json metric (default); finetune / scene = BASELINE.json configs[3] / configs[4]; "
+                         "feed / gwpca = the SURVEY 8(f) preprocessing paths; all but pretrain run on 1 GPU")
+    ap.add_argument("--labelled", type=int, default=32)
+    ap.add_argument("--unlabelled", type=int, default=71)
+    ap.add_argument("--scene-batch", type=int, default=16384)
+    ap.add_argument("--no-graph", action="store_true", help="finetune: eager launches instead of the captured CUDA graph")
     ap.add_argument("--fused-optimizer", action="store_true",
                     help="opt-in hsimae_b200.optim.FusedAdamW instead of the driver's torch.optim.AdamW (SURVEY 8f-3; not the default metric)")
     args = ap.parse_args()
@@ -371,7 +628,7 @@ def main():
     if args.workload != "pretrain":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py (impl ours) needs a CUDA device; the product path has no CPU fallback")
-        return feed_main(args) if args.workload == "feed" else gwpca_main(args)
+        return {"feed": feed_main, "gwpca": gwpca_main, "finetune": finetune_main, "scene": scene_main}[args.workload](args)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -390,9 +647,10 @@ def main():
     torch.manual_seed(42); random.seed(42)
     model = Models.HSIMAE(**LARGE).to(dev)
     model.train()
+    dp_parity = None
     if world > 1:
         dp.broadcast_parameters(model)
-        dp.attach(model)
+        dp_parity, _ = dp_parity_check(model, rank, world, dev)   # attaches the gradient exchange
     no_decay = ["bias", "norm"]
     groups = [{"params": [p for n, p in model.named_parameters() if not any(nd in n for nd in no_decay)], "weight_decay": 5e-2},
               {"params": [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
@@ -503,13 +761,14 @@ def main():
                            "optimizer": "hsimae_b200.optim.FusedAdamW (opt-in)" if args.fused_optimizer else "torch.optim.AdamW (driver-owned, unchanged)"},
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": B * CUBE * 4,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps},
-                "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "loss": last_loss,
+                "dp_parity_max_rel": dp_parity, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "loss": last_loss,
                 "clocks": clocks,
                 "step_tensor_frac": {"achieved_tflops": B * FLOP_PER_PATCH / (ms * 1e-3) / 1e12, "peak_tflops": pk["tf_sus"],
                                      "frac": B * FLOP_PER_PATCH / (ms * 1e-3) / 1e12 / pk["tf_sus"], "peak": "sustained, " + pk["src"]}}
     if world > 1:
         dist.barrier()
     if rank == 0 and not args.no_roofline:
+        line["kernel_accounting"] = step_kernel_accounting(lambda: step(pool[0]), B, pk)
         del pool, bufs
         opt.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()

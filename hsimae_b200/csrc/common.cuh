@@ -41,12 +41,16 @@ const char* last_error();
 // Programmatic dependent launch (see gemm_tc.cu): kernels launched through launch_pdl may begin while the previous
 // kernel on the stream drains; they call pdl_wait() before touching global memory and pdl_trigger() when their own
 // dependents may be scheduled.  HSIMAE_PDL=0 launches them as ordinary stream-ordered kernels.
+// HSIMAE_PDL=0 (environment, default on) or hsimae_set_pdl() at run time (per-kernel timing: overlapped prologues make
+// activity-profiler durations of consecutive kernels overlap)
+bool pdl_enabled();
+void set_pdl(bool on);
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <class Kernel, class... Args>
 inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
-  static const bool pdl = !(getenv("HSIMAE_PDL") && atoi(getenv("HSIMAE_PDL")) == 0);
+  const bool pdl = pdl_enabled();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -587,7 +587,7 @@ int launch_clustered(Kernel kernel, int grid, int threads, size_t smem, int P, c
   attr[0].val.clusterDim.x = P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  static const bool pdl = !(getenv("HSIMAE_PDL") && atoi(getenv("HSIMAE_PDL")) == 0);
+  const bool pdl = pdl_enabled();
   cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
   HS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
   return kOk;

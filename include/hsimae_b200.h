@@ -145,6 +145,10 @@ typedef struct hsimae_gemm_desc {
 } hsimae_gemm_desc;
 int hsimae_gemm(const hsimae_gemm_desc* d, void* stream);
 
+/* Programmatic dependent launch of the library's kernels on (default, HSIMAE_PDL=0 disables) / off; returns the previous
+ * setting.  Off is for per-kernel timing: overlapped prologues make consecutive kernels' profiler durations overlap. */
+int hsimae_set_pdl(int on);
+
 /* W[Nout,Kin] += Y[Mred,Nout]^T X[Mred,Kin] (+ column sums of Y into bias).  row_map 1 = interleaved w1|w3 rows. */
 typedef struct hsimae_wgrad_desc {
   int32_t Mred, Nout, Kin, impl;

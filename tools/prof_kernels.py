@@ -16,6 +16,8 @@ gw1, gw3, gb1, gb3 = (torch.zeros(684, D, device=dev) for _ in range(2)) , None,
 gw1, gw3 = torch.zeros(684, D, device=dev), torch.zeros(684, D, device=dev)
 gb1, gb3 = torch.zeros(684, device=dev), torch.zeros(684, device=dev)
 w2t = bf(H, D) * 0.05
+x2 = bf(M, D)
+b13, b2 = torch.zeros(2 * H, device=dev), torch.zeros(D, device=dev)
 w13t = bf(D, 2 * H) * 0.05
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 for _ in range(reps):
@@ -23,7 +25,7 @@ for _ in range(reps):
     ops.gemm(x, wqkv, ops.EPI_BIAS_BF16)                                      # qkv projection
     ops.gemm(x, w13, ops.EPI_SWIGLU, keep_ab=False)                           # gated up-projection (training path: g only)
     ops.gemm(g, w2, ops.EPI_RESID_LN, resid=resid, gamma=gamma, beta=beta)    # down-projection + residual + LN
-    ops.gemm(x, w2t, ops.EPI_DGATE, A2=x, B2=w13)                             # d(gate), a|b recomputed
+    ops.gemm(x, w2t, ops.EPI_DGATE, A2=x2, B2=w13)                            # d(gate), a|b recomputed (two distinct activations)
     ops.gemm(dab, w13t, ops.EPI_BIAS_BF16)                                    # dgrad K=1376
     ops.wgrad(dab, x, gw1, dst1=gw3, row_map=1, rows_valid=684, bias0=gb1, bias1=gb3)   # dW13
     ops.wgrad(x, g, torch.zeros(D, 684, device=dev), cols_valid=684, bias0=torch.zeros(D, device=dev))  # dW2
@@ -31,6 +33,8 @@ for _ in range(reps):
     ops.attention_backward(qkv, out, lse, x, B, D, 16, 18, 1, 18, 18, 1)
     out, lse = ops.attention_forward(qkv, B, D, 16, 18, 3, 6, 6, 1)          # spatial
     out, lse = ops.attention_forward(qkv, B, D, 16, 18, 6, 3, 1, 6)          # spectral
+    ops.mlp_fused(x, w13, b13, w2, b2, resid, gamma=gamma, beta=beta)         # fused gated MLP (training: g kept)
+    ops.mlp_fused(x, w13, b13, w2, b2, resid, gamma=gamma, beta=beta, keep_g=False)   # fused gated MLP (inference)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 print("done")
