@@ -133,10 +133,17 @@ loss_kernel(LossArgs a) {
   float* sCube = sm;                  // input cube
   float* sPred = sCube + g.cube;      // de-normalised prediction, cube layout
   float* sMask = sPred + g.cube;      // mask, cube layout
+  // cube offset of element j of patch p, built once per CTA: the (t, h, w, u, p, q) index arithmetic is five runtime
+  // integer divisions per element, which was most of this kernel's instruction stream (139 -> see profiles/r02*)
+  unsigned short* sIdx = reinterpret_cast<unsigned short*>(sMask + g.cube);   // [P][PK]
   __shared__ float swl[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int PK = g.PK;
   const float inv_pk = 1.0f / PK;
+  for (int i = threadIdx.x; i < g.P * PK; i += blockDim.x) {
+    const int p = i / PK, j = i - p * PK;
+    sIdx[i] = (unsigned short)cube_index2(g, p, j);
+  }
   for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     __syncthreads();
     const float4* src = reinterpret_cast<const float4*>(a.imgs + (size_t)n * g.cube);
@@ -146,12 +153,12 @@ loss_kernel(LossArgs a) {
     for (int p = warp; p < g.P; p += nw) {
       const size_t m = (size_t)n * g.P + p;
       const float mk = a.mask[m];
-      float t[4]; int idx[4];
+      float t[4], pr[4]; int idx[4];
       float s = 0.f;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int j = lane + 32 * r;
-        if (j < PK) { idx[r] = cube_index2(g, p, j); t[r] = sCube[idx[r]]; s += t[r]; } else { idx[r] = 0; t[r] = 0.f; }
+        if (j < PK) { idx[r] = sIdx[p * PK + j]; t[r] = sCube[idx[r]]; s += t[r]; pr[r] = a.pred[m * a.ldp + j]; } else { idx[r] = 0; t[r] = 0.f; pr[r] = 0.f; }
       }
       float mean = 0.f, std = 1.f;
       if (a.norm_pix) {
@@ -169,12 +176,11 @@ loss_kernel(LossArgs a) {
       for (int r = 0; r < 4; ++r) {
         const int j = lane + 32 * r;
         if (j < PK) {
-          const float pr = a.pred[m * a.ldp + j];
           const float tn = (t[r] - mean) * istd;
-          const float df = pr - tn;
+          const float df = pr[r] - tn;
           l = fmaf(df, df, l);
           if (a.dpred) a.dpred[m * a.ldd + j] = __float2bfloat16_rn(gsc * df);
-          sPred[idx[r]] = fmaf(pr, std, mean);
+          sPred[idx[r]] = fmaf(pr[r], std, mean);
           sMask[idx[r]] = mk;
         } else if (j < a.ldd && a.dpred) {
           a.dpred[m * a.ldd + j] = __float2bfloat16_rn(0.f);
@@ -221,7 +227,8 @@ int launch_loss(const LossArgs& a, cudaStream_t stream) {
   HS_REQUIRE(a.g.cube % 4 == 0, "loss: cube size must be a multiple of 4");
   HS_REQUIRE(a.mask_sum > 0.f, "loss: no masked patches");
   if (a.N == 0) return kOk;
-  const size_t smem = (size_t)3 * a.g.cube * sizeof(float);
+  HS_REQUIRE(a.g.cube < 65536, "loss: cube of %d elements unsupported", a.g.cube);
+  const size_t smem = (size_t)3 * a.g.cube * sizeof(float) + (size_t)a.g.P * a.g.PK * sizeof(unsigned short);
   HS_CHECK_CUDA(cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = a.N < 8 * kNumSMs ? a.N : 8 * kNumSMs;
   loss_kernel<<<grid, 256, smem, stream>>>(a);

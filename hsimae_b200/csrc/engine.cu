@@ -54,7 +54,8 @@ struct hsimae_plan {
   int64_t w_de, w_de_t, w_pred, w_pred_t;
   int p_pe_w, p_pe_b, p_norm_w, p_norm_b, p_cls_w, p_cls_b, p_de_w, p_de_b, p_dnorm_w, p_dnorm_b, p_pred_w, p_pred_b;
   int64_t grad_elems, bf16_elems, f32_elems;
-  int64_t bucket_end[4];  // gradient-arena boundaries in backward-completion order (see hsimae_plan_grad_bucket)
+  int64_t bucket_end[6];  // gradient-arena boundaries (see hsimae_plan_grad_bucket): the spatial encoder is cut into three
+  int sp_cut[2];          // first spatial block of the middle / last third (backward sub-stages 8 / 4)
   int max_job_elems;
   std::vector<const void*> last_ptrs;
   const void* last_table;
@@ -185,10 +186,19 @@ int build_plan(const hsimae_dims& dm, hsimae_plan* p) {
   p->f_pe_w = b.take_f((int64_t)D * g.PK); p->f_pe_b = b.take_f(D); p->f_pos = b.take_f((int64_t)g.P * D);
   b.vec(p->p_pe_w, p->f_pe_w, D * g.PK); b.vec(p->p_pe_b, p->f_pe_b, D); b.vec(p_pos, p->f_pos, g.P * D);
   const bool qb = dm.qkv_bias != 0;
-  for (int i = 0; i < dm.s_depth; ++i) p->b1.push_back(b.block("blocks_1." + std::to_string(i) + ".", D, p->H, p->Hp, qb));
-  p->bucket_end[0] = align_up(b.gr, 4);   // patch embedding + spatial encoder
+  // the spatial encoder is the LAST thing backward finishes: its gradients go out in three pieces so that only the
+  // all-reduce of the final third of the blocks (+ patch embedding) cannot hide behind compute
+  p->sp_cut[0] = dm.s_depth / 3; p->sp_cut[1] = 2 * dm.s_depth / 3;
+  for (int i = 0; i < dm.s_depth; ++i) {
+    if (i == p->sp_cut[0]) p->bucket_end[0] = align_up(b.gr, 4);   // patch embedding + spatial blocks [0, cut0)
+    if (i == p->sp_cut[1]) p->bucket_end[1] = align_up(b.gr, 4);   // spatial blocks [cut0, cut1)
+    p->b1.push_back(b.block("blocks_1." + std::to_string(i) + ".", D, p->H, p->Hp, qb));
+  }
+  if (dm.s_depth <= p->sp_cut[0]) p->bucket_end[0] = align_up(b.gr, 4);
+  if (dm.s_depth <= p->sp_cut[1]) p->bucket_end[1] = align_up(b.gr, 4);
+  p->bucket_end[2] = align_up(b.gr, 4);   // spatial blocks [cut1, s_depth)
   for (int i = 0; i < dm.s_depth; ++i) p->b2.push_back(b.block("blocks_2." + std::to_string(i) + ".", D, p->H, p->Hp, qb));
-  p->bucket_end[1] = align_up(b.gr, 4);   // spectral encoder
+  p->bucket_end[3] = align_up(b.gr, 4);   // spectral encoder
   for (int i = 0; i < p->n_fusion; ++i) p->bf.push_back(b.block("blocks." + std::to_string(i) + ".", D, p->H, p->Hp, qb));
   p->p_norm_w = b.add_slot("norm.weight", D, true);
   p->p_norm_b = b.add_slot("norm.bias", D, true);
@@ -201,7 +211,7 @@ int build_plan(const hsimae_dims& dm, hsimae_plan* p) {
     p->f_cls_w = b.take_f((int64_t)dm.num_class * g.T * D); p->f_cls_b = b.take_f(dm.num_class);
     b.vec(p->p_cls_w, p->f_cls_w, dm.num_class * g.T * D); b.vec(p->p_cls_b, p->f_cls_b, dm.num_class);
   }
-  p->bucket_end[2] = align_up(b.gr, 4);   // fusion blocks + final norm + classification head
+  p->bucket_end[4] = align_up(b.gr, 4);   // fusion blocks + final norm + classification head
   p->p_de_w = -1;
   if (Dd > 0) {
     p->p_de_w = b.add_slot("decoder_embed.weight", (int64_t)Dd * D, true);
@@ -223,7 +233,7 @@ int build_plan(const hsimae_dims& dm, hsimae_plan* p) {
     b.job(p->p_pred_w, p->w_pred, g.PK, Dd, Dd, 1); b.job(p->p_pred_w, p->w_pred_t, g.PK, Dd, p->PKp, 2);
   }
   p->grad_elems = align_up(b.gr, 4);
-  p->bucket_end[3] = p->grad_elems;       // decoder
+  p->bucket_end[5] = p->grad_elems;       // decoder
   p->bf16_elems = align_up(b.wb, 64);
   p->f32_elems = align_up(b.wf, 16);
   return kOk;
@@ -543,7 +553,7 @@ int64_t hsimae_plan_pack_table_bytes(const hsimae_plan* p) {
   return p ? (int64_t)(p->jobs.size() * sizeof(PackJob) + (size_t)pack_tiles(p) * sizeof(int)) : 0;
 }
 int hsimae_plan_grad_bucket(const hsimae_plan* p, int i, int64_t* offset, int64_t* elems) {
-  HS_REQUIRE(p && offset && elems && i >= 0 && i < 4, "grad_bucket: bad argument");
+  HS_REQUIRE(p && offset && elems && i >= 0 && i < 6, "grad_bucket: bad argument");
   const int64_t begin = i == 0 ? 0 : p->bucket_end[i - 1];
   *offset = begin; *elems = p->bucket_end[i] - begin;
   return kOk;
@@ -714,19 +724,19 @@ int hsimae_encoder_backward(hsimae_plan* p, const void* wb, const void* wf, cons
                             i == sd - 1 ? b.dxA : b.dxB, b.dxB, b));
     }
     }  // stage 2
-    // spatial encoder: in place on dxA
-    if (stages & 4) {
-    HS_TRY(launch_scale_cast(b.dxA, b.dxb, (int)L.M, D, rs2_of(0, sd - 1), c.st));
+    // spatial encoder: in place on dxA, in three sub-stages (4: last third of the blocks, 8: middle, 16: first third)
+    if (stages & 4) HS_TRY(launch_scale_cast(b.dxA, b.dxb, (int)L.M, D, rs2_of(0, sd - 1), c.st));
     for (int i = sd - 1; i >= 0; --i) {
+      const int bit = i >= p->sp_cut[1] ? 4 : (i >= p->sp_cut[0] ? 8 : 16);
+      if (!(stages & bit)) continue;
       const float* x_in = i > 0 ? L.sp[i - 1].x_out : L.x0;
       RowScale prev = i > 0 ? rs2_of(0, i - 1) : none;
       HS_TRY(block_backward(c, p->b1[i], L.M, n, D, p->H, p->Hp, p->heads, ch[0].seq, L.sp[i], x_in, rs1_of(0, i), prev, i > 0,
                             b.dxA, b.dxA, b));
     }
-    }  // stage 4
     dx_embed_b = b.dxB;
   }
-  if (!(stages & 4)) return kOk;
+  if (!(stages & 16)) return kOk;
   EmbedBwdArgs e{};
   e.g = p->g; e.N = n; e.K = L.K; e.D = D; e.imgs = imgs; e.ids_keep = ids; e.dx_a = dx_embed_a; e.dx_b = dx_embed_b;
   e.dW = gptr(c, p->p_pe_w); e.dbias = gptr(c, p->p_pe_b);

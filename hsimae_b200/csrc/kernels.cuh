@@ -49,6 +49,11 @@ struct EmbedBwdArgs {
   float* dbias;                // [D] accumulated
 };
 int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream);
+// tensor-core (TF32 mma.sync) forms for the reference's 8x3x3 patch geometry (embed_mma.cu); the launchers above pick them
+bool embed_fwd_mma_supported(const EmbedArgs& a);
+int launch_embed_fwd_mma(const EmbedArgs& a, cudaStream_t stream);
+bool embed_bwd_mma_supported(const EmbedBwdArgs& a);
+int launch_embed_bwd_mma(const EmbedBwdArgs& a, cudaStream_t stream);
 
 // ---- LayerNorm backward (+ residual-gradient add) ---------------------------
 struct LnBwdArgs {

@@ -334,6 +334,7 @@ int launch_embed_fwd(const EmbedArgs& a, cudaStream_t stream) {
   HS_REQUIRE((a.imgs != nullptr) != (a.scene != nullptr), "embed: exactly one of imgs / scene must be given");
   if (a.scene) HS_REQUIRE(a.g.bands % 4 == 0 && a.scene_w >= a.g.img, "embed: scene needs bands %% 4 == 0 and width >= window");
   if (a.N == 0) return kOk;
+  if (embed_fwd_mma_supported(a)) return launch_embed_fwd_mma(a, stream);
   const size_t smem = embed_fwd_smem(a);
   HS_REQUIRE(smem <= 227 * 1024, "embed: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
   const int grid = a.N < kNumSMs ? a.N : kNumSMs;
@@ -476,6 +477,7 @@ embed_bwd_fixed_kernel(EmbedBwdArgs a) {
 int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream) {
   HS_REQUIRE(a.g.PK <= kMaxPK, "embed_bwd: patch of %d elements unsupported (max %d)", a.g.PK, kMaxPK);
   if (a.N == 0) return kOk;
+  if (embed_bwd_mma_supported(a)) return launch_embed_bwd_mma(a, stream);
   const size_t smem = (size_t)a.g.cube * sizeof(float) + ((size_t)a.K * a.g.PK + a.K) * sizeof(int);
   HS_REQUIRE(smem <= 227 * 1024, "embed_bwd: needs %zu bytes of shared memory", smem);
   const int grid = a.N < 2 * kNumSMs ? a.N : 2 * kNumSMs;   // two CTAs per SM

@@ -4,7 +4,7 @@ One process per GPU; every rank holds a full replica and its own shard of the
 batch.  The only exchange step is the mean of the parameter gradients.  The
 native backward produces all gradients in ONE fp32 arena whose regions become
 final in a known order (decoder -> fusion blocks + final norm -> spectral encoder
--> spatial encoder + patch embedding, see hsimae_plan_grad_bucket), so each
+-> spatial encoder in thirds, the first third with the patch embedding, see hsimae_plan_grad_bucket), so each
 region is all-reduced on NCCL's stream as soon as the stage that finishes it
 has been enqueued, overlapping with the remaining backward kernels.  The
 reference has no counterpart (single device, Model_Pretraining.py:59).

@@ -129,7 +129,7 @@ class _Runtime:
         self.grad_off = [L.hsimae_plan_param_grad_offset(self.plan, i) for i in range(self.n_params)]
         self.grad_elems = L.hsimae_plan_grad_arena_elems(self.plan)
         self.buckets = []
-        for i in range(4):
+        for i in range(6):   # arena order: pe + spatial thirds (0, 1, 2), spectral (3), fusion + norm + head (4), decoder (5)
             off, n = C.c_int64(), C.c_int64()
             _lib.check(L.hsimae_plan_grad_bucket(self.plan, i, C.byref(off), C.byref(n)), "grad_bucket")
             self.buckets.append((off.value, n.value))
@@ -198,7 +198,7 @@ class _Runtime:
         _lib.check(self.lib.hsimae_encoder_forward(self.plan, _ptr(self.wb), _ptr(self.wf), _ptr(imgs), n, lt, ll, _ptr(ids32),
                                                    tab, int(save), _ptr(ws), ws.numel(), _stream()), "encoder_forward")
 
-    def encoder_backward(self, imgs, n, lt, ll, ids32, drops, ws, grads, stages=7):
+    def encoder_backward(self, imgs, n, lt, ll, ids32, drops, ws, grads, stages=31):
         tab = self.drop_table(drops)
         _lib.check(self.lib.hsimae_encoder_backward(self.plan, _ptr(self.wb), _ptr(self.wf), _ptr(imgs), n, lt, ll, _ptr(ids32),
                                                     tab, _ptr(ws), ws.numel(), _ptr(grads), stages, _stream()),
@@ -271,8 +271,10 @@ class _HsiFunction(torch.autograd.Function):
                                                       _ptr(s.ws_enc), _ptr(s.ws_dec), s.ws_dec.numel(), _ptr(g), _ptr(grads),
                                                       _stream()), "decoder_backward")
             if sync is not None and g_logits is None:
-                sync.ready(3)
-            for stage, bucket in ((1, 2), (2, 1), (4, 0)):
+                sync.ready(5)
+            # backward-completion order of the arena regions; the spatial encoder goes out in thirds so that only the
+            # last one (+ the patch embedding) is exposed after the final kernel
+            for stage, bucket in ((1, 4), (2, 3), (4, 2), (8, 1), (16, 0)):
                 rt.encoder_backward(s.imgs_m, s.n_m, s.lt, s.ll, s.keep32, s.drops_m, s.ws_enc, grads, stage)
                 if sync is not None and g_logits is None:
                     sync.ready(bucket)
@@ -281,9 +283,9 @@ class _HsiFunction(torch.autograd.Function):
             T, Lp = rt.dims.bands // rt.dims.b_patch_size, (rt.dims.img_size // rt.dims.patch_size) ** 2
             _lib.check(rt.lib.hsimae_head_backward(rt.plan, _ptr(rt.wf), s.n_full, _ptr(s.ws_full), _ptr(s.pooled), _ptr(gl),
                                                    _ptr(grads), _stream()), "head_backward")
-            rt.encoder_backward(s.imgs_full, s.n_full, T, Lp, None, s.drops_full, s.ws_full, grads, 7)
+            rt.encoder_backward(s.imgs_full, s.n_full, T, Lp, None, s.drops_full, s.ws_full, grads, 31)
             if sync is not None:
-                for b in (3, 2, 1, 0):
+                for b in (5, 4, 3, 2, 1, 0):
                     sync.ready(b)
         if sync is not None:
             sync.finish()

@@ -99,8 +99,9 @@ int hsimae_encoder_forward_scene(hsimae_plan* plan, const void* bf16_arena, cons
                                  int32_t scene_h, int32_t scene_w, int64_t pixel0, int32_t n, void* ws, int64_t ws_bytes,
                                  void* stream);
 /* consumes the latent gradient left in the workspace by decoder/head backward.
- * `stages` is a bit mask (1: final norm + fusion blocks, 2: spectral encoder,
- * 4: spatial encoder + patch embedding); stages must be run in that order, 7 = all. */
+ * `stages` is a bit mask (1: final norm + fusion blocks, 2: spectral encoder, 4 / 8 / 16: last / middle / first third of
+ * the spatial encoder, 16 also the patch embedding); stages must be run in that order, HSIMAE_STAGES_ALL = all. */
+#define HSIMAE_STAGES_ALL 31
 int hsimae_encoder_backward(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, const float* imgs, int32_t n,
                             int32_t len_t, int32_t len_l, const int32_t* ids_keep32, const float* const* drop, void* ws,
                             int64_t ws_bytes, float* grad_arena, int32_t stages, void* stream);

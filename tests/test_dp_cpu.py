@@ -33,21 +33,24 @@ def _worker(rank, world, port, out):
 
         sync = dp.attach(model)
         rt = model._runtime()
-        assert sum(n for _, n in sync.buckets) == rt.grad_elems and len(sync.buckets) == 4
+        assert sum(n for _, n in sync.buckets) == rt.grad_elems and len(sync.buckets) == 6
         grads = torch.arange(rt.grad_elems, dtype=torch.float32) * (rank + 1)
         step = sync.begin(grads)
-        for b in (3, 2, 1):                     # backward-completion order; bucket 0 is flushed by finish()
+        for b in (5, 4, 3, 2, 1):               # backward-completion order; bucket 0 is flushed by finish()
             step.ready(b)
-        step.ready(3)                           # idempotent
+        step.ready(5)                           # idempotent
         step.finish()
         expect = torch.arange(rt.grad_elems, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
         assert torch.allclose(grads, expect)
-        # decoder bucket is the tail of the arena, patch-embed + spatial encoder the head
-        off3, n3 = sync.buckets[3]
-        assert off3 + n3 == rt.grad_elems and sync.buckets[0][0] == 0
+        # decoder bucket is the tail of the arena, patch-embed + the first third of the spatial encoder the head
+        off5, n5 = sync.buckets[5]
+        assert off5 + n5 == rt.grad_elems and sync.buckets[0][0] == 0
         named = dict(zip(rt.names, rt.grad_off))
-        assert named["decoder_pred.weight"] >= off3 and named["patch_embed.proj.weight"] < sync.buckets[0][1]
-        assert sync.buckets[1][0] <= named["blocks_2.0.attn.q.weight"] < sync.buckets[2][0] <= named["blocks.0.attn.q.weight"] < off3
+        assert named["decoder_pred.weight"] >= off5 and named["patch_embed.proj.weight"] < sync.buckets[0][1]
+        sd = TINY["s_depth"]
+        assert named["blocks_1.0.attn.q.weight"] < sync.buckets[1][0] or sd < 3
+        assert sync.buckets[2][0] <= named[f"blocks_1.{sd - 1}.attn.q.weight"] < sync.buckets[3][0]
+        assert sync.buckets[3][0] <= named["blocks_2.0.attn.q.weight"] < sync.buckets[4][0] <= named["blocks.0.attn.q.weight"] < off5
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
