@@ -451,7 +451,11 @@ def finetune_main(args):
     dev = torch.device("cuda", 0)
     torch.manual_seed(0); random.seed(0)
     model = Models.DualViT(**DUAL).to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-2)
+    if args.fused_optimizer:
+        from hsimae_b200.optim import FusedAdamW
+        opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=5e-2)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-2)
     crit = torch.nn.CrossEntropyLoss(ignore_index=0)
     nl, nu = args.labelled, args.unlabelled
     hx, hxu = torch.randn(nl, 1, 32, 9, 9).pin_memory(), torch.randn(nu, 1, 32, 9, 9).pin_memory()
@@ -489,7 +493,8 @@ def finetune_main(args):
             "data": "synthetic",
             "config": {"workload": f"Model_Finetuning.py:147-166 step, {nl} labelled + {nu} unlabelled 9x9x32 tiles, 17 classes, mask 0.8, "
                                    "lambda 10, drop_path 0.2 (BASELINE.json configs[3])",
-                       "execution": "one CUDA graph per visible shape (hsimae_b200.graph)" if stepper is not None else "eager launches"},
+                       "execution": "one CUDA graph per visible shape (hsimae_b200.graph)" if stepper is not None else "eager launches",
+                       "optimizer": "hsimae_b200.optim.FusedAdamW (opt-in)" if args.fused_optimizer else "torch.optim.AdamW (driver-owned, unchanged)"},
             "e2e": {"value": (nl + nu) / (e2e_ms * 1e-3), "unit": "patches/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": (nl + nu) * CUBE * 4 + nl * 8, "d2h_bytes_per_step": nl * 17 * 4},
             "gpu_launches_per_step": launches,

@@ -365,6 +365,16 @@ bool fused_mlp_enabled() {
   return on;
 }
 
+// The recompute-in-backward d(gate) kernel and the fused MLP kernel walk ALL hidden chunks of a row tile inside one CTA:
+// serial latency when there are only a few row tiles (fine-tuning batches: 1152 rows = 9 tiles, d(gate) 29 us).  Keeping
+// the pre-activations and using the per-output-tile kernels for such problems was measured and is NOT faster end to end
+// (fine-tuning step 9.9 -> 10.3 ms: one more launch and the [M, 2Hp] write in forward): HSIMAE_RECOMPUTE_MIN_ROWS (default 0)
+// keeps the switch for A/B measurements.  The choice depends on M only, so forward and backward agree.
+bool recompute_gate_for(const hsimae_plan* p, int64_t M) {
+  static const int min_rows = getenv("HSIMAE_RECOMPUTE_MIN_ROWS") ? atoi(getenv("HSIMAE_RECOMPUTE_MIN_ROWS")) : 0;
+  return p->recompute_gate && M >= min_rows;
+}
+
 int run_gemm(const Ctx& c, GemmArgs& a, int epi) {
   a.ln_eps = 1e-5f;
   if (c.p->debug_simt) return gemm_simt(a, epi, c.simt, c.st);
@@ -404,7 +414,8 @@ int block_forward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int Hp
   dn.M = (int)M; dn.N = d; dn.K = Hp; dn.A = s.g; dn.lda = Hp; dn.B = c.wb + w.w2; dn.ldb = Hp;
   dn.out0 = s.x_out; dn.ld0 = d; dn.bias = c.wf + w.b2; dn.resid = s.x_mid; dn.ldr = d; dn.resid2 = tail.resid2; dn.rs = rs2;
   dn.gamma = tail.gamma; dn.beta = tail.beta; dn.out1 = tail.ln; dn.ld1 = d; dn.stats = tail.stats; dn.ln_eps = 1e-5f;
-  if (!c.p->debug_simt && c.p->recompute_gate && fused_mlp_enabled() && mlp_fused_supported(d, Hp)) {
+  const bool recompute = recompute_gate_for(c.p, M);
+  if (!c.p->debug_simt && recompute && fused_mlp_enabled() && mlp_fused_supported(d, Hp)) {
     // one kernel; the gate output is only written when backward will read it (dW2)
     MlpFusedArgs m{};
     m.tail = dn; m.X = s.ln2; m.ldx = d; m.W13 = c.wb + w.w13; m.ldw = d; m.b13 = c.wf + w.b13;
@@ -415,7 +426,7 @@ int block_forward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int Hp
   a = GemmArgs{};
   a.M = (int)M; a.N = 2 * Hp; a.K = d; a.A = s.ln2; a.lda = d; a.B = c.wb + w.w13; a.ldb = d;
   // the pre-activations are only kept for the checker path; the product path recomputes them in backward
-  a.out0 = c.p->recompute_gate ? nullptr : s.ab; a.ld0 = 2 * Hp; a.out1 = s.g; a.ld1 = Hp; a.bias = c.wf + w.b13;
+  a.out0 = recompute ? nullptr : s.ab; a.ld0 = 2 * Hp; a.out1 = s.g; a.ld1 = Hp; a.bias = c.wf + w.b13;
   HS_TRY(run_gemm(c, a, kEpiSwiGLU));
   HS_TRY(run_gemm(c, dn, kEpiResidLN));
   return kOk;
@@ -430,7 +441,7 @@ int block_backward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int H
   // d(gate): dab = dswiglu(dxb W2, ab)
   a.M = (int)M; a.N = Hp; a.K = d; a.A = b.dxb; a.lda = d; a.B = c.wb + w.w2_t; a.ldb = d;
   a.out0 = b.dab; a.ld0 = 2 * Hp;
-  if (c.p->recompute_gate) {
+  if (recompute_gate_for(c.p, M)) {
     a.A2 = s.ln2; a.lda2 = d; a.B2 = c.wb + w.w13; a.ldb2 = d; a.bias = c.wf + w.b13;
     HS_TRY(run_gemm(c, a, kEpiDGate));
   } else {

@@ -16,6 +16,12 @@ COMBOS = [
     {"HSIMAE_PDL": "0", "HSIMAE_ATTN_SMALL": "0"},               # plain launches, mma attention for short groups
     {"HSIMAE_GEMM_ARES": "0", "HSIMAE_WGRAD_FUSED_BIAS": "0"},   # streaming kernels only, separate bias-gradient kernel
     {"HSIMAE_GEMM_ARES_N": "128", "HSIMAE_GEMM_ARES_N_GATE": "256"},
+    # round 2: the fused gated-MLP kernel with eight final-epilogue warps / in its single-CTA form; the two-launch MLP and
+    # the CUDA-core patch embedding; saved pre-activations + per-output-tile kernels below a row threshold
+    {"HSIMAE_FUSED_MLP_FW": "8"},
+    {"HSIMAE_FUSED_MLP_PAIR": "0"},
+    {"HSIMAE_FUSED_MLP": "0", "HSIMAE_EMBED_MMA": "0"},
+    {"HSIMAE_RECOMPUTE_MIN_ROWS": "8192"},
 ]
 
 
