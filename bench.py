@@ -300,7 +300,7 @@ def step_kernel_accounting(step_fn, batch: int, pk):
     for e in evs:
         a = agg.setdefault(e.name, [0, 0.0])
         a[0] += 1; a[1] += e.device_time   # us
-    fam = {"gemm": ("gemm_tc", "mlp_fused", "wgrad_tc"), "attention": ("attn_",), "ln_bwd": ("ln_bwd",), "embed": ("embed_",),
+    fam = {"gemm": ("gemm_tc", "mlp_fused", "wgrad_"), "attention": ("attn_",), "ln_bwd": ("ln_bwd",), "embed": ("embed_",),
            "loss": ("loss_kernel",), "fill": ("fill_",), "mask": ("mask_kernel",), "pack": ("pack_kernel",), "nccl": ("nccl",)}
     fams = {k: [0, 0.0] for k in fam}; fams["other (optimizer, rand, casts)"] = [0, 0.0]
     for name, (n, us) in agg.items():

@@ -96,6 +96,7 @@ PROTOTYPES = {
     "hsimae_head_backward": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsimae_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "hsimae_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
+    "hsimae_wgrad_group": (c_int, [C.POINTER(WgradDesc), c_i32, c_void_p]),
     "hsimae_mlp_fused": (c_int, [C.POINTER(MlpDesc), c_void_p]),
     "hsimae_set_pdl": (c_int, [c_int]),
     "hsimae_attention_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,

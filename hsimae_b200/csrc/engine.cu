@@ -276,12 +276,14 @@ void take_chain(Bump& b, std::vector<BlockStash>& v, int nblk, bool save, int64_
 
 struct BwdScratch {
   float* dxA; float* dxB; bf16* dxb; bf16* dab; bf16* dln; bf16* dqkv; bf16* dao;
+  bf16* dxb2;   // bf16(rs1 * dx_mid): kept apart from dxb so that the block's four weight gradients can run as one launch
 };
 
 BwdScratch take_bwd(Bump& b, int64_t M, int d, int Hp) {
   BwdScratch s;
   s.dxA = b.take<float>(M * d); s.dxB = b.take<float>(M * d); s.dxb = b.take<bf16>(M * d);
   s.dab = b.take<bf16>(M * 2 * Hp); s.dln = b.take<bf16>(M * d); s.dqkv = b.take<bf16>(M * 3 * d); s.dao = b.take<bf16>(M * d);
+  s.dxb2 = b.take<bf16>(M * d);
   return s;
 }
 
@@ -384,6 +386,11 @@ int run_wgrad(const Ctx& c, const WgradArgs& a) {
   if (c.p->debug_simt) return wgrad_simt(a, c.st);
   return wgrad_tc(a, c.st);
 }
+// the weight gradients of one block: one grouped launch (every operand stays live until the end of the block's backward)
+int run_wgrad_group(const Ctx& c, const WgradArgs* jobs, int n) {
+  if (c.p->debug_simt) { for (int i = 0; i < n; ++i) HS_TRY(wgrad_simt(jobs[i], c.st)); return kOk; }
+  return wgrad_tc_group(jobs, n, c.st);
+}
 
 struct TailLN {
   const float* gamma; const float* beta;  // nullptr: no LayerNorm after the block
@@ -448,45 +455,48 @@ int block_backward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int H
     a.ab = s.ab; a.ldab = 2 * Hp;
     HS_TRY(run_gemm(c, a, kEpiDSwiGLU));
   }
-  WgradArgs g{};
-  g.Mred = (int)M; g.Nout = d; g.Kin = Hp; g.Y = b.dxb; g.ldy = d; g.X = s.g; g.ldx = Hp;
-  g.dst0 = gptr(c, w.w2w); g.ld = H; g.rows_valid = d; g.cols_valid = H; g.bias0 = gptr(c, w.w2b);
-  HS_TRY(run_wgrad(c, g));
+  WgradArgs wj[4];
+  WgradArgs& g2 = wj[0];
+  g2 = WgradArgs{};
+  g2.Mred = (int)M; g2.Nout = d; g2.Kin = Hp; g2.Y = b.dxb; g2.ldy = d; g2.X = s.g; g2.ldx = Hp;
+  g2.dst0 = gptr(c, w.w2w); g2.ld = H; g2.rows_valid = d; g2.cols_valid = H; g2.bias0 = gptr(c, w.w2b);
   // d(ln2) = dab W13
   a = GemmArgs{};
   a.M = (int)M; a.N = d; a.K = 2 * Hp; a.A = b.dab; a.lda = 2 * Hp; a.B = c.wb + w.w13_t; a.ldb = 2 * Hp;
   a.out0 = b.dln; a.ld0 = d;
   HS_TRY(run_gemm(c, a, kEpiBiasBf16));
-  g = WgradArgs{};
-  g.Mred = (int)M; g.Nout = 2 * Hp; g.Kin = d; g.Y = b.dab; g.ldy = 2 * Hp; g.X = s.ln2; g.ldx = d;
-  g.dst0 = gptr(c, w.w1w); g.dst1 = gptr(c, w.w3w); g.ld = d; g.row_map = 1; g.rows_valid = H; g.cols_valid = d;
-  g.bias0 = gptr(c, w.w1b); g.bias1 = gptr(c, w.w3b);
-  HS_TRY(run_wgrad(c, g));
-  // norm2 backward + residual; emits bf16(rs1 * dx_mid)
+  WgradArgs& g13 = wj[1];
+  g13 = WgradArgs{};
+  g13.Mred = (int)M; g13.Nout = 2 * Hp; g13.Kin = d; g13.Y = b.dab; g13.ldy = 2 * Hp; g13.X = s.ln2; g13.ldx = d;
+  g13.dst0 = gptr(c, w.w1w); g13.dst1 = gptr(c, w.w3w); g13.ld = d; g13.row_map = 1; g13.rows_valid = H; g13.cols_valid = d;
+  g13.bias0 = gptr(c, w.w1b); g13.bias1 = gptr(c, w.w3b);
+  // norm2 backward + residual; emits bf16(rs1 * dx_mid) into its own buffer (dxb is still the dW2 operand)
   LnBwdArgs ln{};
   ln.M = (int)M; ln.D = d; ln.dy = b.dln; ln.x = s.x_mid; ln.stats = s.stats2; ln.gamma = c.wf + w.g2;
-  ln.dx_in = dx_src; ln.dx_out = dx_dst; ln.dxb = b.dxb; ln.rs = rs1; ln.dgamma = gptr(c, w.n2w); ln.dbeta = gptr(c, w.n2b);
+  ln.dx_in = dx_src; ln.dx_out = dx_dst; ln.dxb = b.dxb2; ln.rs = rs1; ln.dgamma = gptr(c, w.n2w); ln.dbeta = gptr(c, w.n2b);
   HS_TRY(launch_ln_bwd(ln, c.st));
   // attention output projection
   a = GemmArgs{};
-  a.M = (int)M; a.N = d; a.K = d; a.A = b.dxb; a.lda = d; a.B = c.wb + w.wproj_t; a.ldb = d; a.out0 = b.dao; a.ld0 = d;
+  a.M = (int)M; a.N = d; a.K = d; a.A = b.dxb2; a.lda = d; a.B = c.wb + w.wproj_t; a.ldb = d; a.out0 = b.dao; a.ld0 = d;
   HS_TRY(run_gemm(c, a, kEpiBiasBf16));
-  g = WgradArgs{};
-  g.Mred = (int)M; g.Nout = d; g.Kin = d; g.Y = b.dxb; g.ldy = d; g.X = s.ao; g.ldx = d;
-  g.dst0 = gptr(c, w.pw); g.ld = d; g.rows_valid = d; g.cols_valid = d; g.bias0 = gptr(c, w.pb);
-  HS_TRY(run_wgrad(c, g));
+  WgradArgs& gp = wj[2];
+  gp = WgradArgs{};
+  gp.Mred = (int)M; gp.Nout = d; gp.Kin = d; gp.Y = b.dxb2; gp.ldy = d; gp.X = s.ao; gp.ldx = d;
+  gp.dst0 = gptr(c, w.pw); gp.ld = d; gp.rows_valid = d; gp.cols_valid = d; gp.bias0 = gptr(c, w.pb);
   // attention backward
   AttnArgs at{}; at.N = N; at.D = d; at.heads = heads; at.s = seq; at.qkv = s.qkv; at.out = s.ao; at.lse = s.lse;
   at.dout = b.dao; at.dqkv = b.dqkv;
   HS_TRY(launch_attn_bwd(at, c.st));
+  WgradArgs& gq = wj[3];
+  gq = WgradArgs{};
+  gq.Mred = (int)M; gq.Nout = 3 * d; gq.Kin = d; gq.Y = b.dqkv; gq.ldy = 3 * d; gq.X = s.ln1; gq.ldx = d;
+  gq.dst0 = gptr(c, w.qw); gq.ld = d; gq.rows_valid = 3 * d; gq.cols_valid = d; gq.bias0 = gptr(c, w.qb);
+  // dW2 | dW1,dW3 | dWproj | dWq,k,v (+ their bias gradients): one launch, one wave
+  HS_TRY(run_wgrad_group(c, wj, 4));
   // q|k|v projection
   a = GemmArgs{};
   a.M = (int)M; a.N = d; a.K = 3 * d; a.A = b.dqkv; a.lda = 3 * d; a.B = c.wb + w.wqkv_t; a.ldb = 3 * d; a.out0 = b.dln; a.ld0 = d;
   HS_TRY(run_gemm(c, a, kEpiBiasBf16));
-  g = WgradArgs{};
-  g.Mred = (int)M; g.Nout = 3 * d; g.Kin = d; g.Y = b.dqkv; g.ldy = 3 * d; g.X = s.ln1; g.ldx = d;
-  g.dst0 = gptr(c, w.qw); g.ld = d; g.rows_valid = 3 * d; g.cols_valid = d; g.bias0 = gptr(c, w.qb);
-  HS_TRY(run_wgrad(c, g));
   // norm1 backward + residual; emits bf16(rs_prev * dx_in) for the previous block
   ln = LnBwdArgs{};
   ln.M = (int)M; ln.D = d; ln.dy = b.dln; ln.x = x_in; ln.stats = s.stats1; ln.gamma = c.wf + w.g1;
@@ -938,6 +948,19 @@ int hsimae_wgrad(const hsimae_wgrad_desc* d, void* stream) {
   a.bias0 = d->bias0; a.bias1 = d->bias1;
   if (d->impl == 1) return wgrad_simt(a, (cudaStream_t)stream);
   return wgrad_tc(a, (cudaStream_t)stream);
+}
+
+int hsimae_wgrad_group(const hsimae_wgrad_desc* d, int32_t n, void* stream) {
+  HS_REQUIRE(d != nullptr && n >= 1 && n <= 4, "wgrad_group: 1..4 descriptors");
+  WgradArgs jobs[4];
+  for (int i = 0; i < n; ++i) {
+    WgradArgs& a = jobs[i];
+    a = WgradArgs{};
+    a.Mred = d[i].Mred; a.Nout = d[i].Nout; a.Kin = d[i].Kin; a.Y = (const bf16*)d[i].Y; a.ldy = d[i].ldy; a.X = (const bf16*)d[i].X; a.ldx = d[i].ldx;
+    a.dst0 = d[i].dst0; a.dst1 = d[i].dst1; a.ld = d[i].ld; a.row_map = d[i].row_map; a.rows_valid = d[i].rows_valid; a.cols_valid = d[i].cols_valid;
+    a.bias0 = d[i].bias0; a.bias1 = d[i].bias1;
+  }
+  return wgrad_tc_group(jobs, n, (cudaStream_t)stream);
 }
 
 int hsimae_attention_forward(const void* qkv, void* out, float* lse, int32_t n, int32_t D, int32_t heads, int32_t K, int32_t nseq,

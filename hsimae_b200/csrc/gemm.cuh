@@ -64,6 +64,7 @@ __host__ __device__ inline int packed_col(int which, int h) { return (h / kGate)
 int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream);
 int gemm_simt(const GemmArgs& a, int epi, float* scratch, cudaStream_t stream);
 int wgrad_tc(const WgradArgs& a, cudaStream_t stream);
+int wgrad_tc_group(const WgradArgs* jobs, int njobs, cudaStream_t stream);   // up to 4 independent problems in one launch
 int wgrad_simt(const WgradArgs& a, cudaStream_t stream);
 
 }  // namespace hsimae

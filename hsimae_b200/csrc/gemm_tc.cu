@@ -744,6 +744,186 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------
+// grouped wgrad: up to kMaxWgradJobs independent W += Y^T X problems in ONE launch (the four weight gradients of a
+// transformer block: each alone is one partial wave with its own launch, drain and tail -- dWproj reaches 360 TFLOP/s
+// on its own).  Same CTA program as wgrad_tc_kernel; a CTA (pair) looks its (job, tile, split) up in the job table.
+// ---------------------------------------------------------------------------
+constexpr int kMaxWgradJobs = 4;
+struct WgradJob {
+  WgradArgs p;
+  int bn, tiles_c, num_tiles, kb_total, kb_per_split;
+  int unit0;   // first unit (CTA or CTA pair) of this job in the launch
+};
+struct alignas(64) WgradGroupParams {
+  CUtensorMap tmY[kMaxWgradJobs], tmX[kMaxWgradJobs];
+  WgradJob job[kMaxWgradJobs];
+  int njobs;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+wgrad_group_kernel(const __grid_constant__ WgradGroupParams gp, int stages, uint32_t stage_bytes, uint32_t lbo, uint32_t sbo,
+                   uint32_t kstep_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = P == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int unit = (int)blockIdx.x / P;
+  int ji = 0;
+#pragma unroll
+  for (int j = 1; j < kMaxWgradJobs; ++j)
+    if (j < gp.njobs && unit >= gp.job[j].unit0) ji = j;
+  const WgradJob& J = gp.job[ji];
+  const WgradArgs& p = J.p;
+  const CUtensorMap* tmY = &gp.tmY[ji];
+  const CUtensorMap* tmX = &gp.tmX[ji];
+  const int bn = J.bn;
+  const int bn_cta = bn / P;                                    // X columns staged by this CTA
+  const uint32_t a_bytes = 2 * kBoxBytes;
+  const uint32_t b_bytes = (uint32_t)(bn_cta / 64) * kBoxBytes;
+  const uint32_t job_stage_bytes = a_bytes + b_bytes;           // <= stage_bytes (the widest job of the launch)
+  uint8_t* ones = smem + (size_t)stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + kOnesBytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int local = unit - J.unit0;
+  const int tile = local % J.num_tiles;
+  const int split = local / J.num_tiles;
+  const int r_blk = tile / J.tiles_c, c_blk = tile - r_blk * J.tiles_c;
+  const int row0 = (r_blk * P + crank) * kBlockM;               // first output row of this CTA
+  const int kb0 = split * J.kb_per_split;
+  int kb1 = kb0 + J.kb_per_split; if (kb1 > J.kb_total) kb1 = J.kb_total;
+  const int nkb = kb1 - kb0;
+  const bool do_bias = p.bias0 != nullptr && c_blk == 0;
+
+  if (do_bias) {
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // bf16 1.0 x2
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(tmY);
+    ptx::prefetch_tmap(tmX);
+    for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    ptx::mbar_init(tfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    if constexpr (P == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  }
+  ptx::pdl_trigger();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (P == 2) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (ptx::elect_one()) {
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(empty + stage, phase ^ 1u);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          if constexpr (P == 2) {
+            if (crank == 0) ptx::mbar_expect_tx(full + stage, 2u * job_stage_bytes);
+            const uint32_t bar = ptx::mapa_rank(ptx::smem_u32(full + stage), 0);
+            for (int j = 0; j < 2; ++j) ptx::tma_load_2d_pair(sa + j * kBoxBytes, tmY, bar, row0 + j * 64, kb * 64);
+            for (int j = 0; j < bn_cta / 64; ++j)
+              ptx::tma_load_2d_pair(sa + a_bytes + j * kBoxBytes, tmX, bar, c_blk * bn + crank * bn_cta + j * 64, kb * 64);
+          } else {
+            ptx::mbar_expect_tx(full + stage, job_stage_bytes);
+            for (int j = 0; j < 2; ++j) ptx::tma_load_2d(sa + j * kBoxBytes, tmY, full + stage, row0 + j * 64, kb * 64);
+            for (int j = 0; j < bn / 64; ++j)
+              ptx::tma_load_2d(sa + a_bytes + j * kBoxBytes, tmX, full + stage, c_blk * bn + j * 64, kb * 64);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (crank == 0 && ptx::elect_one()) {
+        const uint32_t idesc = make_idesc(bn, true, true, kBlockM * P);
+        const uint32_t idesc_ones = make_idesc(16, true, true, kBlockM * P);
+        const uint64_t ones_desc = make_smem_desc(ptx::smem_u32(ones), lbo, sbo);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(full + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * kstep_bytes, lbo, sbo);
+            const uint64_t bdesc = make_smem_desc(sa + a_bytes + k * kstep_bytes, lbo, sbo);
+            if constexpr (P == 2) {
+              ptx::umma_bf16_pair(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (do_bias) ptx::umma_bf16_pair(tmem_base + 256, adesc, ones_desc, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+            } else {
+              ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (do_bias) ptx::umma_bf16(tmem_base + 256, adesc, ones_desc, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          if constexpr (P == 2) ptx::umma_commit_pair(empty + stage); else ptx::umma_commit(empty + stage);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        if constexpr (P == 2) ptx::umma_commit_pair(tfull); else ptx::umma_commit(tfull);
+      }
+    } else {
+      const int q = warp & 3;
+      ptx::mbar_wait(tfull, 0);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int r = row0 + q * 32 + lane;  // packed output row
+      float* drow = nullptr;
+      float* brow = nullptr;
+      if (r < p.Nout) {
+        if (p.row_map == 0) {
+          if (r < p.rows_valid) { drow = p.dst0 + (size_t)r * p.ld; brow = p.bias0 ? p.bias0 + r : nullptr; }
+        } else {
+          const int which = (r % (2 * kGate)) / kGate;
+          const int h = (r / (2 * kGate)) * kGate + (r % kGate);
+          if (h < p.rows_valid) {
+            drow = (which ? p.dst1 : p.dst0) + (size_t)h * p.ld;
+            brow = p.bias0 ? (which ? p.bias1 : p.bias0) + h : nullptr;
+          }
+        }
+      }
+      for (int c = 0; c < bn; c += 16) {
+        float v[16];
+        ptx::tmem_ld16(tbase + c, v);
+        ptx::tmem_ld_wait();
+        const int col = c_blk * bn + c;
+        if (drow != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            if (col + i < p.cols_valid) red_add_f32x4(drow + col + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      if (do_bias) {
+        float v[16];
+        ptx::tmem_ld16(tbase + 256, v);
+        ptx::tmem_ld_wait();
+        if (brow != nullptr) atomicAdd(brow, v[0]);
+      }
+    }
+  }
+
+  ptx::pdl_trigger();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (P == 2) ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (P == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // column sums (bias gradients): dst[map(n)] += sum_m Y[m][n]
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -1130,12 +1310,89 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   return kOk;
 }
 
+
+// output-column tile of a weight-gradient problem: multiple of 64 (of 128 for CTA pairs), at most 256
+void wgrad_tiling(const WgradArgs& a, int P, int* bn, int* tiles_c, int* tiles_r) {
+  const int kin64 = ceil_div(a.Kin, 64) * 64;
+  *tiles_c = ceil_div(kin64, 256);
+  *bn = ceil_div(kin64 / 64, *tiles_c) * 64;
+  if (P == 2 && *bn % 128 != 0) *bn += 64;
+  *tiles_r = ceil_div(a.Nout, kBlockM * P);
+}
+
+template <int P>
+int launch_wgrad_group(const WgradArgs* jobs, int njobs, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    HS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_group_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  WgradGroupParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.njobs = njobs;
+  int tiles[kMaxWgradJobs], total_tiles = 0, bn_max = 0;
+  for (int j = 0; j < njobs; ++j) {
+    WgradJob& J = gp.job[j];
+    J.p = jobs[j];
+    int tiles_r;
+    wgrad_tiling(jobs[j], P, &J.bn, &J.tiles_c, &tiles_r);
+    J.num_tiles = tiles_r * J.tiles_c;
+    J.kb_total = ceil_div(jobs[j].Mred, 64);
+    tiles[j] = J.num_tiles; total_tiles += J.num_tiles;
+    if (J.bn > bn_max) bn_max = J.bn;
+    HS_TRY(get_tmap(jobs[j].Y, (uint64_t)jobs[j].Nout, (uint64_t)jobs[j].Mred, (uint64_t)jobs[j].ldy, 64, 64, &gp.tmY[j]));
+    HS_TRY(get_tmap(jobs[j].X, (uint64_t)jobs[j].Kin, (uint64_t)jobs[j].Mred, (uint64_t)jobs[j].ldx, 64, 64, &gp.tmX[j]));
+  }
+  // one wave: split every tile's reduction so that the launch has at most one CTA (pair) per SM (pair); every tile is the
+  // same amount of work per reduction row, so the splits are handed out evenly and the remainder goes to the first jobs
+  const int units_max = kNumSMs / P;
+  int base = units_max / total_tiles; if (base < 1) base = 1;
+  int extra = base * total_tiles < units_max ? (units_max - base * total_tiles) : 0;
+  int unit = 0;
+  for (int j = 0; j < njobs; ++j) {
+    WgradJob& J = gp.job[j];
+    int splits = base;
+    if (extra >= tiles[j]) { splits += 1; extra -= tiles[j]; }
+    if (splits > J.kb_total) splits = J.kb_total;
+    J.kb_per_split = ceil_div(J.kb_total, splits);
+    splits = ceil_div(J.kb_total, J.kb_per_split);
+    J.unit0 = unit;
+    unit += J.num_tiles * splits;
+  }
+  const int stage_bytes = (2 + bn_max / P / 64) * kBoxBytes;
+  int stages = (kSmemBudget - kOnesBytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  const size_t smem = (size_t)stages * stage_bytes + kOnesBytes + 1024 + 256;
+  const uint32_t lbo = kBoxBytes, sbo = 1024, kstep = 2048;   // MN-major SWIZZLE_128B canonical layout, see launch_wgrad
+  HS_TRY(launch_clustered(wgrad_group_kernel<P>, unit * P, kGemmThreads, smem, P, stream, gp, stages, (uint32_t)stage_bytes, lbo, sbo, kstep));
+  HS_CHECK_LAUNCH("wgrad_group_kernel");
+  return kOk;
+}
+
 int wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
   HS_TRY(wgrad_check_args(a));
   // CTA pairs halve the L2 reads of X (re-read by every row tile); they need at least two row tiles' worth of rows
   static const int pair = env_int("HSIMAE_WGRAD_PAIR", 1);
   if (pair != 0 && a.Nout > 2 * kBlockM && a.Mred >= 64 * kNumSMs) return launch_wgrad<2>(a, stream);
   return launch_wgrad<1>(a, stream);
+}
+
+// The weight gradients of one block in one launch.  HSIMAE_WGRAD_GROUP=0: one launch per problem (A/B measurements).
+int wgrad_tc_group(const WgradArgs* jobs, int njobs, cudaStream_t stream) {
+  HS_REQUIRE(njobs >= 1 && njobs <= kMaxWgradJobs, "wgrad group: %d jobs (1..%d supported)", njobs, kMaxWgradJobs);
+  for (int j = 0; j < njobs; ++j) HS_TRY(wgrad_check_args(jobs[j]));
+  static const int group = env_int("HSIMAE_WGRAD_GROUP", 1);
+  static const bool fused_bias = env_int("HSIMAE_WGRAD_FUSED_BIAS", 1) != 0;
+  if (group == 0 || !fused_bias || njobs == 1) {
+    for (int j = 0; j < njobs; ++j) HS_TRY(wgrad_tc(jobs[j], stream));
+    return kOk;
+  }
+  static const int pair = env_int("HSIMAE_WGRAD_PAIR", 1);
+  bool any_tall = false;
+  int mred_min = jobs[0].Mred;
+  for (int j = 0; j < njobs; ++j) { any_tall |= jobs[j].Nout > 2 * kBlockM; if (jobs[j].Mred < mred_min) mred_min = jobs[j].Mred; }
+  if (pair != 0 && any_tall && mred_min >= 64 * kNumSMs) return launch_wgrad_group<2>(jobs, njobs, stream);
+  return launch_wgrad_group<1>(jobs, njobs, stream);
 }
 
 }  // namespace hsimae

@@ -122,6 +122,22 @@ def wgrad(Y, X, dst0, *, impl=IMPL_TC, dst1=None, row_map=0, rows_valid=None, co
     _lib.check(L.hsimae_wgrad(C.byref(d), _stream()), "wgrad")
 
 
+def wgrad_group(jobs):
+    """several `wgrad` problems in one launch; `jobs` = list of dicts with the keyword arguments of `wgrad` (Y, X, dst0, ...)"""
+    L = _lib.load()
+    arr = (_lib.WgradDesc * len(jobs))()
+    for d, j in zip(arr, jobs):
+        Y, X, dst0 = j["Y"], j["X"], j["dst0"]
+        _need_cuda(Y, X, dst0)
+        d.Mred, d.Nout, d.Kin, d.impl = Y.shape[0], Y.shape[1], X.shape[1], 0
+        d.Y, d.ldy, d.X, d.ldx = _p(Y), Y.stride(0), _p(X), X.stride(0)
+        d.dst0, d.dst1, d.ld, d.row_map = _p(dst0), _p(j.get("dst1")), dst0.stride(0), j.get("row_map", 0)
+        d.rows_valid = j.get("rows_valid", dst0.shape[0])
+        d.cols_valid = j.get("cols_valid", dst0.shape[1])
+        d.bias0, d.bias1 = _p(j.get("bias0")), _p(j.get("bias1"))
+    _lib.check(L.hsimae_wgrad_group(arr, len(jobs), _stream()), "wgrad_group")
+
+
 def attention_forward(qkv, n, D, heads, K, nseq, length, seq_step, tok_step):
     _need_cuda(qkv)
     L = _lib.load()

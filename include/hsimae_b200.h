@@ -159,6 +159,8 @@ typedef struct hsimae_wgrad_desc {
   float* bias0; float* bias1;
 } hsimae_wgrad_desc;
 int hsimae_wgrad(const hsimae_wgrad_desc* d, void* stream);
+/* up to 4 independent problems (the weight gradients of one block) in ONE launch, one wave over the SMs */
+int hsimae_wgrad_group(const hsimae_wgrad_desc* d, int32_t n, void* stream);
 
 /* Gated MLP half of a block as ONE kernel (csrc/block_fused.cu; replaces the kEpiSwiGLU + kEpiResidLN pair of launches;
  * /root/reference/Models.py:231-232 SwiGLU.forward + the residual add of Block.forward :305):

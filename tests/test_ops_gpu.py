@@ -286,6 +286,41 @@ def test_attention_fwd_bwd(ops, n, D, heads, lt, ll, kind):
     assert rel_err(dqkv.float(), leaf.grad) < 2e-2   # bf16 O/dO inputs + bf16 output
 
 
+@pytest.mark.parametrize("M,d,H", [(73728 // 4, 256, 684), (40000, 64, 172), (700, 128, 344)])
+def test_wgrad_group_matches_single_launches(ops, M, d, H):
+    """The four weight gradients of a block (dW2, dW1|dW3, dWproj, dWq|k|v + bias gradients) in one grouped launch ==
+    the same four problems launched one by one == torch fp32 on the same bf16 operands."""
+    hp = (H + 15) // 16 * 16
+    dy, g = _rand_bf16(M, d, scale=0.1, seed=1), _rand_bf16(M, hp, scale=0.5, seed=2)
+    dab, ln2 = _rand_bf16(M, 2 * hp, scale=0.1, seed=3), _rand_bf16(M, d, seed=4)
+    dxm, ao = _rand_bf16(M, d, scale=0.1, seed=5), _rand_bf16(M, d, seed=6)
+    dqkv, ln1 = _rand_bf16(M, 3 * d, scale=0.1, seed=7), _rand_bf16(M, d, seed=8)
+
+    def fresh():
+        z = lambda *s: torch.zeros(*s, device=DEV)
+        return dict(w2=z(d, H), b2=z(d), w1=z(H, d), w3=z(H, d), b1=z(H), b3=z(H), wp=z(d, d), bp=z(d), wq=z(3 * d, d), bq=z(3 * d))
+
+    def jobs(o):
+        return [dict(Y=dy, X=g, dst0=o["w2"], cols_valid=H, bias0=o["b2"]),
+                dict(Y=dab, X=ln2, dst0=o["w1"], dst1=o["w3"], row_map=1, rows_valid=H, bias0=o["b1"], bias1=o["b3"]),
+                dict(Y=dxm, X=ao, dst0=o["wp"], bias0=o["bp"]),
+                dict(Y=dqkv, X=ln1, dst0=o["wq"], bias0=o["bq"])]
+    a, b = fresh(), fresh()
+    ops.wgrad_group(jobs(a))
+    for j in jobs(b):
+        ops.wgrad(j.pop("Y"), j.pop("X"), j.pop("dst0"), **j)
+    for k in a:
+        assert rel_err(a[k], b[k]) < 2e-5, k          # same MMAs, different reduction-split boundaries / atomic order
+    assert rel_err(a["w2"], dy.float().t() @ g.float()[:, :H]) < 2e-4
+    assert rel_err(a["wp"], dxm.float().t() @ ao.float()) < 2e-4
+    assert rel_err(a["wq"], dqkv.float().t() @ ln1.float()) < 2e-4
+    assert rel_err(a["bq"], dqkv.float().sum(0)) < 2e-4
+    idx = torch.arange(H, device=DEV)
+    ca, cb = (idx // 16) * 32 + idx % 16, (idx // 16) * 32 + 16 + idx % 16
+    assert rel_err(a["w1"], dab.float()[:, ca].t() @ ln2.float()) < 2e-4
+    assert rel_err(a["w3"], dab.float()[:, cb].t() @ ln2.float()) < 2e-4
+
+
 # ---------------------------------------------------------------- fused gated MLP (csrc/block_fused.cu)
 @pytest.mark.parametrize("M,d,H,pair", [(1000, 256, 684, 1), (300, 64, 172, 1), (129, 128, 344, 1), (4099, 256, 684, 1), (77, 64, 172, 1),
                                         (128, 64, 172, 1), (37000, 256, 684, 1), (40000, 64, 172, 1), (300, 64, 172, 0), (700, 128, 344, 0)])
