@@ -17,10 +17,15 @@ fill_fwd_kernel(FillArgs a) {
   const int D = a.D, K = a.K, P = a.P;
   float* sy = sm;                 // [K][D]
   float* smean = sy + (size_t)K * D;  // [D]
+  int* ssrc = reinterpret_cast<int*>(smean + D);   // [P] ids_restore of the sample: staged with the tokens, so that the
+                                                   // per-token loop below has no dependent global load in it
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int vecs = D / 4;   // D % 4 == 0 (decoder widths are multiples of 16)
   for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     __syncthreads();
-    for (int i = threadIdx.x; i < K * D; i += blockDim.x) sy[i] = a.y[(size_t)n * K * D + i];
+    const float4* src4 = reinterpret_cast<const float4*>(a.y + (size_t)n * K * D);
+    for (int i = threadIdx.x; i < K * vecs; i += blockDim.x) reinterpret_cast<float4*>(sy)[i] = ld_stream_f4(src4 + i);
+    for (int p = threadIdx.x; p < P; p += blockDim.x) ssrc[p] = a.ids_restore[(size_t)n * P + p];
     __syncthreads();
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
       float s = 0.f;
@@ -29,7 +34,7 @@ fill_fwd_kernel(FillArgs a) {
     }
     __syncthreads();
     for (int p = warp; p < P; p += nw) {
-      const int src = a.ids_restore[(size_t)n * P + p];
+      const int src = ssrc[p];
       const float* row = src < K ? sy + (size_t)src * D : smean;
       const size_t m = (size_t)n * P + p;
       float v[8];
@@ -66,18 +71,23 @@ fill_bwd_kernel(FillArgs a) {
   float* sdx = sm;                    // [P][D]
   float* sacc = sdx + (size_t)P * D;  // [D]
   int* spos = reinterpret_cast<int*>(sacc + D);  // [K]
+  int* ssrc = spos + K;                          // [P] ids_restore of the sample (no global loads inside the reductions)
   for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     __syncthreads();
-    for (int i = threadIdx.x; i < P * D; i += blockDim.x) sdx[i] = a.dx[(size_t)n * P * D + i];
+    {
+      const float4* src4 = reinterpret_cast<const float4*>(a.dx + (size_t)n * P * D);
+      for (int i = threadIdx.x; i < P * D / 4; i += blockDim.x) reinterpret_cast<float4*>(sdx)[i] = ld_stream_f4(src4 + i);
+    }
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
       const int src = a.ids_restore[(size_t)n * P + p];
+      ssrc[p] = src;
       if (src < K) spos[src] = p;
     }
     __syncthreads();
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
       float s = 0.f;
       for (int p = 0; p < P; ++p)
-        if (a.ids_restore[(size_t)n * P + p] >= K) s += sdx[p * D + d];
+        if (ssrc[p] >= K) s += sdx[p * D + d];
       sacc[d] = s / K;
     }
     __syncthreads();
@@ -91,7 +101,8 @@ fill_bwd_kernel(FillArgs a) {
 int launch_fill_fwd(const FillArgs& a, cudaStream_t stream) {
   HS_REQUIRE(a.D <= 256, "decoder fill: D=%d > 256 unsupported", a.D);
   if (a.N == 0) return kOk;
-  const size_t smem = ((size_t)a.K * a.D + a.D) * sizeof(float);
+  HS_REQUIRE(a.D % 4 == 0, "decoder fill: D=%d must be a multiple of 4", a.D);
+  const size_t smem = ((size_t)a.K * a.D + a.D) * sizeof(float) + (size_t)a.P * sizeof(int);
   HS_CHECK_CUDA(cudaFuncSetAttribute(fill_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = a.N < 8 * kNumSMs ? a.N : 8 * kNumSMs;
   fill_fwd_kernel<<<grid, 256, smem, stream>>>(a);
@@ -101,7 +112,7 @@ int launch_fill_fwd(const FillArgs& a, cudaStream_t stream) {
 
 int launch_fill_bwd(const FillArgs& a, cudaStream_t stream) {
   if (a.N == 0) return kOk;
-  const size_t smem = ((size_t)a.P * a.D + a.D) * sizeof(float) + (size_t)a.K * sizeof(int);
+  const size_t smem = ((size_t)a.P * a.D + a.D) * sizeof(float) + (size_t)(a.K + a.P) * sizeof(int);
   HS_CHECK_CUDA(cudaFuncSetAttribute(fill_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = a.N < 8 * kNumSMs ? a.N : 8 * kNumSMs;
   fill_bwd_kernel<<<grid, 256, smem, stream>>>(a);
