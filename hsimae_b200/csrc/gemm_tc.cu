@@ -1192,6 +1192,10 @@ int pick_block_n(int N, int K, int epi) {
   static const int wide = getenv("HSIMAE_GEMM_ARES_N") ? atoi(getenv("HSIMAE_GEMM_ARES_N")) : 256;
   static const int wide_gate = getenv("HSIMAE_GEMM_ARES_N_GATE") ? atoi(getenv("HSIMAE_GEMM_ARES_N_GATE")) : 128;
   if (K <= 256 && N >= 512 && epi == kEpiBiasBf16 && wide == 256) return 256;
+  // square short-K projections (attention-output dgrad, [M,256] x [256,256]): one 256-column tile on the streaming pair
+  // kernel instead of two 128-column tiles on the A-resident one (HSIMAE_GEMM_N256=0 restores it; A/B measurements)
+  static const int n256 = getenv("HSIMAE_GEMM_N256") ? atoi(getenv("HSIMAE_GEMM_N256")) : 1;
+  if (n256 && K <= 256 && N == 256 && epi == kEpiBiasBf16) return 256;
   if (K <= 256 && N >= 512 && (epi == kEpiSwiGLU || epi == kEpiDSwiGLU) && wide_gate == 256) return 256;
   // otherwise four 128-column accumulator stages (four epilogue warp groups).  Tiles start at multiples of 128 so
   // the 128-byte output boxes never straddle two tiles; the N tail is clipped by TMA.
@@ -1212,7 +1216,7 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   const bool ares = use_ares(a, epi, block_n, n_blks);
   // the 256-column residual epilogue keeps 96 KB of residual boxes: only a pair's half-size weight tiles leave a useful ring
   const bool pair = use_pair(block_n, m_blks, a.K, a.N, ares, epi == kEpiSwiGLU && a.out0 == nullptr) ||
-                    (epi == kEpiResidLN && block_n > 128 && use_pair(block_n, m_blks, 512, a.N, false, false));
+                    ((epi == kEpiResidLN || epi == kEpiBiasBf16) && block_n > 128 && use_pair(block_n, m_blks, 512, a.N, false, false));
   CUtensorMap tm[5];
   HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tm[0]));
   HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(pair ? block_n / 2 : block_n), &tm[1]));
