@@ -1192,9 +1192,10 @@ int pick_block_n(int N, int K, int epi) {
   static const int wide = getenv("HSIMAE_GEMM_ARES_N") ? atoi(getenv("HSIMAE_GEMM_ARES_N")) : 256;
   static const int wide_gate = getenv("HSIMAE_GEMM_ARES_N_GATE") ? atoi(getenv("HSIMAE_GEMM_ARES_N_GATE")) : 128;
   if (K <= 256 && N >= 512 && epi == kEpiBiasBf16 && wide == 256) return 256;
-  // square short-K projections (attention-output dgrad, [M,256] x [256,256]): one 256-column tile on the streaming pair
-  // kernel instead of two 128-column tiles on the A-resident one (HSIMAE_GEMM_N256=0 restores it; A/B measurements)
-  static const int n256 = getenv("HSIMAE_GEMM_N256") ? atoi(getenv("HSIMAE_GEMM_N256")) : 1;
+  // square short-K projections (attention-output dgrad, [M,256] x [256,256]): HSIMAE_GEMM_N256=1 runs them as one 256-column
+  // tile on the streaming pair kernel instead of two 128-column tiles on the A-resident one -- measured slower (18.9 vs
+  // 17.9 us, step 22.4 vs 22.1 ms), kept as a switch
+  static const int n256 = getenv("HSIMAE_GEMM_N256") ? atoi(getenv("HSIMAE_GEMM_N256")) : 0;
   if (n256 && K <= 256 && N == 256 && epi == kEpiBiasBf16) return 256;
   if (K <= 256 && N >= 512 && (epi == kEpiSwiGLU || epi == kEpiDSwiGLU) && wide_gate == 256) return 256;
   // otherwise four 128-column accumulator stages (four epilogue warp groups).  Tiles start at multiples of 128 so
