@@ -99,6 +99,7 @@ PROTOTYPES = {
     "hsimae_wgrad_group": (c_int, [C.POINTER(WgradDesc), c_i32, c_void_p]),
     "hsimae_mlp_fused": (c_int, [C.POINTER(MlpDesc), c_void_p]),
     "hsimae_set_pdl": (c_int, [c_int]),
+    "hsimae_helper_join": (c_int, [c_void_p, c_void_p]),
     "hsimae_attention_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                          c_i32, c_void_p]),
     "hsimae_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32,

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <cstdlib>
+#include <mutex>
 #include "../../include/hsimae_b200.h"
 #include "gemm.cuh"
 #include "block_fused.cuh"
@@ -60,6 +61,7 @@ struct hsimae_plan {
   std::vector<const void*> last_ptrs;
   const void* last_table;
   bool debug_simt;
+  bool helper_pending = false;   // the spectral backward chain is running on the helper stream and has not been joined yet
   bool recompute_gate;   // backward recomputes the gated up-projection instead of re-reading saved pre-activations
 };
 
@@ -293,6 +295,7 @@ struct EncLayout {
   std::vector<BlockStash> sp, sc, fu;
   bf16* latent; float* stats_f; float* x_final;
   bf16* dlatent; BwdScratch bw;
+  BwdScratch bw2; float* dxC;   // split encoders: scratch of the spectral chain when it runs beside the spatial one; spatial gradient stream
   float* simt;
   int64_t bytes;
 };
@@ -310,7 +313,11 @@ EncLayout enc_layout(const hsimae_plan* p, int N, int lt, int ll, bool save, con
   L.stats_f = b.take<float>(L.M * 2);
   L.x_final = !L.fu.empty() ? L.fu.back().x_out : (!L.sc.empty() ? L.sc.back().x_out : L.x0);
   L.dlatent = nullptr; L.bw = BwdScratch{};
-  if (save) { L.dlatent = b.take<bf16>(L.M * D); L.bw = take_bwd(b, L.M, D, p->Hp); }
+  L.bw2 = BwdScratch{}; L.dxC = nullptr;
+  if (save) {
+    L.dlatent = b.take<bf16>(L.M * D); L.bw = take_bwd(b, L.M, D, p->Hp);
+    if (p->dims.s_depth > 0) { L.bw2 = take_bwd(b, L.M, D, p->Hp); L.dxC = b.take<float>(L.M * D); }
+  }
   L.simt = p->debug_simt ? b.take<float>(L.M * (int64_t)(3 * D > 2 * p->Hp ? 3 * D : 2 * p->Hp)) : nullptr;
   L.bytes = align_up(b.off, 256);
   return L;
@@ -375,6 +382,29 @@ bool fused_mlp_enabled() {
 bool recompute_gate_for(const hsimae_plan* p, int64_t M) {
   static const int min_rows = getenv("HSIMAE_RECOMPUTE_MIN_ROWS") ? atoi(getenv("HSIMAE_RECOMPUTE_MIN_ROWS")) : 0;
   return p->recompute_gate && M >= min_rows;
+}
+
+// ---------------------------------------------------------------------------
+// The spatial and the spectral encoder are independent chains of full-device kernels between the patch embedding and
+// the fusion blocks (Models.py:553-564).  Run back to back, every kernel boundary (~2.5 us of drain / launch / fill) and
+// every partial last wave leaves SMs idle; run on TWO streams, the CTAs of one chain's next kernel fill the SMs the other
+// chain's kernel is draining.  The helper stream is forked from and joined back into the caller's stream with events, so
+// the ABI contract (all work ordered on the given stream, capturable) holds.  HSIMAE_OVERLAP=0 disables.
+// ---------------------------------------------------------------------------
+struct Helper { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr, aux = nullptr; bool ok = false; };
+Helper& helper() {
+  static Helper h;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const bool on = !(getenv("HSIMAE_OVERLAP") && atoi(getenv("HSIMAE_OVERLAP")) == 0);
+    if (!on) return;
+    if (cudaStreamCreateWithFlags(&h.st, cudaStreamNonBlocking) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&h.join, cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&h.aux, cudaEventDisableTiming) != cudaSuccess) return;
+    h.ok = true;
+  });
+  return h;
 }
 
 int run_gemm(const Ctx& c, GemmArgs& a, int epi) {
@@ -647,14 +677,26 @@ static int encoder_forward_impl(hsimae_plan* p, const void* wb, const void* wf, 
   }
   HS_TRY(launch_embed_fwd(e, c.st));
 
+  // spatial chain on the caller's stream, spectral chain on the helper stream (see helper())
+  Helper& hp = helper();
+  const bool overlap = split && hp.ok && !p->debug_simt;
+  Ctx cctx[3] = {c, c, c};
+  if (overlap) {
+    cctx[1].st = hp.st;
+    HS_CHECK_CUDA(cudaEventRecord(hp.fork, c.st));
+    HS_CHECK_CUDA(cudaStreamWaitEvent(hp.st, hp.fork, 0));
+  }
   TailLN final_ln{wff + p->f_norm_g, wff + p->f_norm_b, L.latent, L.stats_f, nullptr};
   const float* x_in = L.x0;
   for (int ci = 0; ci < 3; ++ci) {
     ChainSpec& cs = ch[ci];
     const int nb = (int)cs.st->size();
     if (nb == 0) continue;
+    const Ctx& c = cctx[ci];
     if (ci == 1) x_in = L.x0;             // the spectral encoder restarts from the embedded tokens
     for (int i = 0; i < nb; ++i) {
+      // the last spectral block adds the spatial result (x = x1 + x2): it waits for the spatial chain
+      if (overlap && ci == 1 && i == nb - 1) HS_CHECK_CUDA(cudaStreamWaitEvent(hp.st, hp.aux, 0));
       TailLN tail{};
       if (i + 1 < nb) {
         const BlockW& nx = (*cs.w)[i + 1];
@@ -672,6 +714,11 @@ static int encoder_forward_impl(hsimae_plan* p, const void* wb, const void* wf, 
       RowScale rs2 = make_rs(drop, cs.drop_base + 2 * i + 1, cs.mode, L.K, L.ll, cs.G);
       HS_TRY(block_forward(c, (*cs.w)[i], L.M, n, D, p->Hp, p->heads, cs.seq, (*cs.st)[i], x_in, rs1, rs2, tail));
       x_in = (*cs.st)[i].x_out;
+    }
+    if (overlap && ci == 0) HS_CHECK_CUDA(cudaEventRecord(hp.aux, cctx[0].st));           // spatial chain enqueued
+    if (overlap && ci == 1) {                                                             // join: the fusion blocks follow on the caller's stream
+      HS_CHECK_CUDA(cudaEventRecord(hp.join, hp.st));
+      HS_CHECK_CUDA(cudaStreamWaitEvent(cctx[0].st, hp.join, 0));
     }
   }
   return kOk;
@@ -733,19 +780,31 @@ int hsimae_encoder_backward(hsimae_plan* p, const void* wb, const void* wf, cons
   }  // stage 1
   const float* dx_embed_a = b.dxA;
   const float* dx_embed_b = nullptr;
+  Helper& hp = helper();
   if (split) {
     const int sd = (int)L.sp.size();
-    // spectral encoder: reads the summed gradient dxA, writes its own stream dxB
+    // spectral encoder: reads the summed gradient dxA, writes its own stream dxB.  With stage bit 32 it runs on the helper
+    // stream (own scratch) beside the spatial chain and is joined before the patch-embedding backward / by hsimae_helper_join.
     if (stages & 2) {
-    HS_TRY(launch_scale_cast(b.dxA, b.dxb, (int)L.M, D, rs2_of(1, sd - 1), c.st));
-    for (int i = sd - 1; i >= 0; --i) {
-      const float* x_in = i > 0 ? L.sc[i - 1].x_out : L.x0;
-      RowScale prev = i > 0 ? rs2_of(1, i - 1) : none;
-      HS_TRY(block_backward(c, p->b2[i], L.M, n, D, p->H, p->Hp, p->heads, ch[1].seq, L.sc[i], x_in, rs1_of(1, i), prev, i > 0,
-                            i == sd - 1 ? b.dxA : b.dxB, b.dxB, b));
-    }
+      const bool async = (stages & 32) != 0 && hp.ok && !p->debug_simt;
+      Ctx cs = c;
+      BwdScratch& bs = async ? L.bw2 : b;
+      if (async) {
+        HS_CHECK_CUDA(cudaEventRecord(hp.fork, c.st));
+        HS_CHECK_CUDA(cudaStreamWaitEvent(hp.st, hp.fork, 0));
+        cs.st = hp.st;
+      }
+      HS_TRY(launch_scale_cast(b.dxA, bs.dxb, (int)L.M, D, rs2_of(1, sd - 1), cs.st));
+      for (int i = sd - 1; i >= 0; --i) {
+        const float* x_in = i > 0 ? L.sc[i - 1].x_out : L.x0;
+        RowScale prev = i > 0 ? rs2_of(1, i - 1) : none;
+        HS_TRY(block_backward(cs, p->b2[i], L.M, n, D, p->H, p->Hp, p->heads, ch[1].seq, L.sc[i], x_in, rs1_of(1, i), prev, i > 0,
+                              i == sd - 1 ? b.dxA : b.dxB, b.dxB, bs));
+      }
+      if (async) { HS_CHECK_CUDA(cudaEventRecord(hp.join, hp.st)); p->helper_pending = true; }
     }  // stage 2
-    // spatial encoder: in place on dxA, in three sub-stages (4: last third of the blocks, 8: middle, 16: first third)
+    // spatial encoder in three sub-stages (4: last third of the blocks, 8: middle, 16: first third).  Its gradient stream
+    // is dxC: the summed gradient dxA stays read-only, the spectral chain may still be reading it.
     if (stages & 4) HS_TRY(launch_scale_cast(b.dxA, b.dxb, (int)L.M, D, rs2_of(0, sd - 1), c.st));
     for (int i = sd - 1; i >= 0; --i) {
       const int bit = i >= p->sp_cut[1] ? 4 : (i >= p->sp_cut[0] ? 8 : 16);
@@ -753,15 +812,29 @@ int hsimae_encoder_backward(hsimae_plan* p, const void* wb, const void* wf, cons
       const float* x_in = i > 0 ? L.sp[i - 1].x_out : L.x0;
       RowScale prev = i > 0 ? rs2_of(0, i - 1) : none;
       HS_TRY(block_backward(c, p->b1[i], L.M, n, D, p->H, p->Hp, p->heads, ch[0].seq, L.sp[i], x_in, rs1_of(0, i), prev, i > 0,
-                            b.dxA, b.dxA, b));
+                            i == sd - 1 ? b.dxA : L.dxC, L.dxC, b));
     }
+    dx_embed_a = L.dxC;
     dx_embed_b = b.dxB;
   }
   if (!(stages & 16)) return kOk;
+  if (p->helper_pending) {   // the patch-embedding backward sums both chains' gradients
+    HS_CHECK_CUDA(cudaStreamWaitEvent(c.st, hp.join, 0));
+    p->helper_pending = false;
+  }
   EmbedBwdArgs e{};
   e.g = p->g; e.N = n; e.K = L.K; e.D = D; e.imgs = imgs; e.ids_keep = ids; e.dx_a = dx_embed_a; e.dx_b = dx_embed_b;
   e.dW = gptr(c, p->p_pe_w); e.dbias = gptr(c, p->p_pe_b);
   return launch_embed_bwd(e, c.st);
+}
+
+int hsimae_helper_join(hsimae_plan* p, void* stream) {
+  HS_REQUIRE(p != nullptr, "null plan");
+  if (p->helper_pending) {
+    HS_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, helper().join, 0));
+    p->helper_pending = false;
+  }
+  return kOk;
 }
 
 __global__ void latent_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ g,

@@ -274,16 +274,21 @@ class _HsiFunction(torch.autograd.Function):
                 sync.ready(5)
             # backward-completion order of the arena regions; the spatial encoder goes out in thirds so that only the
             # last one (+ the patch embedding) is exposed after the final kernel
-            for stage, bucket in ((1, 4), (2, 3), (4, 2), (8, 1), (16, 0)):
-                rt.encoder_backward(s.imgs_m, s.n_m, s.lt, s.ll, s.keep32, s.drops_m, s.ws_enc, grads, stage)
-                if sync is not None and g_logits is None:
+            # The spectral chain (stage 2 | 32) runs on the library's helper stream beside the spatial thirds and is joined
+            # before the last third: its region (bucket 3) is final on this stream after the join.
+            for stage, bucket in ((1, 4), (2 | 32, None), (4, 2), (8, 1), (-1, 3), (16, 0)):
+                if stage < 0:
+                    _lib.check(rt.lib.hsimae_helper_join(rt.plan, _stream()), "helper_join")
+                else:
+                    rt.encoder_backward(s.imgs_m, s.n_m, s.lt, s.ll, s.keep32, s.drops_m, s.ws_enc, grads, stage)
+                if sync is not None and g_logits is None and bucket is not None:
                     sync.ready(bucket)
         if g_logits is not None and s.ws_full is not None:
             gl = g_logits.detach().to(torch.float32).contiguous()
             T, Lp = rt.dims.bands // rt.dims.b_patch_size, (rt.dims.img_size // rt.dims.patch_size) ** 2
             _lib.check(rt.lib.hsimae_head_backward(rt.plan, _ptr(rt.wf), s.n_full, _ptr(s.ws_full), _ptr(s.pooled), _ptr(gl),
                                                    _ptr(grads), _stream()), "head_backward")
-            rt.encoder_backward(s.imgs_full, s.n_full, T, Lp, None, s.drops_full, s.ws_full, grads, 31)
+            rt.encoder_backward(s.imgs_full, s.n_full, T, Lp, None, s.drops_full, s.ws_full, grads, 31 | 32)
             if sync is not None:
                 for b in (5, 4, 3, 2, 1, 0):
                     sync.ready(b)

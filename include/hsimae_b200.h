@@ -102,6 +102,11 @@ int hsimae_encoder_forward_scene(hsimae_plan* plan, const void* bf16_arena, cons
  * `stages` is a bit mask (1: final norm + fusion blocks, 2: spectral encoder, 4 / 8 / 16: last / middle / first third of
  * the spatial encoder, 16 also the patch embedding); stages must be run in that order, HSIMAE_STAGES_ALL = all. */
 #define HSIMAE_STAGES_ALL 31
+/* Stage bit 32 (with bit 2): run the spectral chain on the library's helper stream beside the spatial chain (forked from `stream`
+ * with an event, own scratch); it is joined back into `stream` before the patch-embedding backward of stage 16, or earlier by
+ * hsimae_helper_join (data-parallel callers: the spectral gradient region is final on `stream` after the join). */
+#define HSIMAE_STAGE_SPECTRAL_ASYNC 32
+int hsimae_helper_join(hsimae_plan* plan, void* stream);
 int hsimae_encoder_backward(hsimae_plan* plan, const void* bf16_arena, const void* f32_arena, const float* imgs, int32_t n,
                             int32_t len_t, int32_t len_l, const int32_t* ids_keep32, const float* const* drop, void* ws,
                             int64_t ws_bytes, float* grad_arena, int32_t stages, void* stream);
