@@ -109,7 +109,7 @@ __device__ __forceinline__ void mlp_final_epilogue(const GemmArgs& p, TmemAcc& a
   if (st.pending) { if (st.leader) ptx::bulk_wait_read0(); __syncwarp(); st.pending = false; }   // every box is free again
   for (int ch = 0; ch < kFinalBoxes && ch < nch; ++ch) issue(ch);
   wait_acc();
-  float sum = 0.f;
+  float sum = 0.f, sumsq = 0.f;
   for (int ch = 0; ch < nch; ++ch) {
     const int b = ch % kFinalBoxes, c = c0 + ch * 32;
     const uint32_t row = st.boxes + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void mlp_final_epilogue(const GemmArgs& p, TmemAcc& a
     }
     if (valid) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sum += v[i];
+      for (int i = 0; i < 32; ++i) { sum += v[i]; sumsq = fmaf(v[i], v[i], sumsq); }
     }
     if (ln) acc.template store<32>(c, v);
 #pragma unroll
@@ -151,22 +151,21 @@ __device__ __forceinline__ void mlp_final_epilogue(const GemmArgs& p, TmemAcc& a
   }
   if (!ln) return;
   acc.fence_store();
-  // row statistics (over BOTH column halves when the row is split between two warps)
+  // Row statistics in ONE pass (sum and sum of squares gathered while the row was drained): a second trip through the
+  // accumulator for the centred sum of squares is 8 more TMEM loads inside the section that holds the accumulator.  The rows
+  // are residual-stream values (|mean| of the order of the standard deviation): E[x^2] - mean^2 loses nothing in fp32 here.
+  // (Over BOTH column halves when the row is split between two warps.)
   const float inv = 1.0f / (float)width;
   if (split) {
     s_red[half * 128 + rowi] = sum;
+    s_red[256 + half * 128 + rowi] = sumsq;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     sum += s_red[(half ^ 1) * 128 + rowi];
+    sumsq += s_red[256 + (half ^ 1) * 128 + rowi];
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the partials may be overwritten by the next tile
   }
   const float mean = sum * inv;
-  float sq = 0.f;
-  for (int c = c0; c < c0 + cw; c += 32) sq += epi_sqdev_chunk<32>(acc, c, mean);
-  if (split) {
-    s_red[256 + half * 128 + rowi] = sq;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    sq += s_red[256 + (half ^ 1) * 128 + rowi];
-  }
-  const float rstd = rsqrtf(sq * inv + p.ln_eps);
+  const float rstd = rsqrtf(fmaxf(sumsq * inv - mean * mean, 0.f) + p.ln_eps);
   if (half == 0 && valid && p.stats) *reinterpret_cast<float2*>(p.stats + 2 * (size_t)m) = make_float2(mean, rstd);
   // bf16 output boxes of 64 columns alternate between the two staging boxes
   if (st.leader) ptx::bulk_wait_read0();
