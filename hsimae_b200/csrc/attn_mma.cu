@@ -234,6 +234,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
   const float scale_log2 = rsqrtf((float)HD) * 1.4426950408889634f;
   const int uph = units_per_head(a.s);
   const int row_vecs = 3 * D / 8;                          // uint4 per token row
+  const FastDiv fd_row(row_vecs), fd_out(D / 8), fd_hg(hgroups);
   Geo<NT> q;
   int cur_u = -1;
 
@@ -243,7 +244,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
     const uint4* src = reinterpret_cast<const uint4*>(a.qkv + (size_t)n0 * K * 3 * D);
     const uint32_t sq_addr = smem_addr(sq);
     for (int i = threadIdx.x; i < ns * K * row_vecs; i += blockDim.x) {
-      const int r = i / row_vecs, c = i - r * row_vecs;
+      int r, c; fd_row.divmod(i, r, c);
       cp_async16(sq_addr + (uint32_t)(r * pitch + c * 16), src + i);
     }
     cp_async_wait_all();
@@ -255,7 +256,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
     const int per_warp = (total + nwarps - 1) / nwarps;
     const int w_end = (warp + 1) * per_warp < total ? (warp + 1) * per_warp : total;
     for (int w = warp * per_warp; w < w_end; ++w) {
-      const int hg = w % hgroups, smp = (w / hgroups) % ns, u = w / (hgroups * ns);
+      int wq, hg, u, smp; fd_hg.divmod(w, wq, hg); FastDiv(ns).divmod(wq, u, smp);
       if (u != cur_u) { q = make_geo<HD, NT>(make_unit(a.s, u), lane, pitch, 0); cur_u = u; }
       uint8_t* ssmp = sq + (size_t)smp * K * pitch;
       const uint32_t sb = smem_addr(ssmp);
@@ -296,7 +297,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
     const int out_vecs = D / 8;
     uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)n0 * K * D);
     for (int i = threadIdx.x; i < ns * K * out_vecs; i += blockDim.x) {
-      const int r = i / out_vecs, c = i - r * out_vecs;
+      int r, c; fd_out.divmod(i, r, c);
       dst[i] = *reinterpret_cast<const uint4*>(sq + (size_t)r * pitch + c * 16);
     }
     if (a.lse) {
@@ -329,6 +330,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
   const float scale_log2 = scale * 1.4426950408889634f;
   const int uph = units_per_head(a.s);
   const int row_vecs = 3 * D / 8, o_vecs = D / 8;
+  const FastDiv fd_row(row_vecs), fd_o(o_vecs), fd_h(H), fd_hg(hgroups);
   Geo<NT> q;
   int cur_u = -1;
 
@@ -339,13 +341,13 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
       const uint32_t sq_addr = smem_addr(sq), sdo_addr = smem_addr(sdo), so_addr = smem_addr(sdq), sl_addr = smem_addr(slse);
       const uint4* src = reinterpret_cast<const uint4*>(a.qkv + (size_t)n0 * K * 3 * D);
       for (int i = threadIdx.x; i < ns * K * row_vecs; i += blockDim.x) {
-        const int r = i / row_vecs, c = i - r * row_vecs;
+        int r, c; fd_row.divmod(i, r, c);
         cp_async16(sq_addr + (uint32_t)(r * pitch + c * 16), src + i);
       }
       const uint4* src2 = reinterpret_cast<const uint4*>(a.dout + (size_t)n0 * K * D);
       const uint4* src3 = reinterpret_cast<const uint4*>(a.out + (size_t)n0 * K * D);   // O parks in the (still unused) dq slot
       for (int i = threadIdx.x; i < ns * K * o_vecs; i += blockDim.x) {
-        const int r = i / o_vecs, c = i - r * o_vecs;
+        int r, c; fd_o.divmod(i, r, c);
         cp_async16(sdo_addr + (uint32_t)(r * pitch_o + c * 16), src2 + i);
         cp_async16(so_addr + (uint32_t)(r * pitch + c * 16), src3 + i);
       }
@@ -355,7 +357,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
       __syncthreads();
       // delta_i = dO_i . O_i per (row, head)
       for (int it = threadIdx.x; it < ns * K * H; it += blockDim.x) {
-        const int h = it % H, r = it / H;
+        int r, h; fd_h.divmod(it, r, h);
         const uint8_t* po = sdq + (size_t)r * pitch + (size_t)h * HD * 2;
         const uint8_t* pd = sdo + (size_t)r * pitch_o + (size_t)h * HD * 2;
         float sacc = 0.f;
@@ -375,7 +377,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
     const int per_warp = (total + nwarps - 1) / nwarps;
     const int w_end = (warp + 1) * per_warp < total ? (warp + 1) * per_warp : total;
     for (int w = warp * per_warp; w < w_end; ++w) {
-      const int hg = w % hgroups, smp = (w / hgroups) % ns, u = w / (hgroups * ns);
+      int wq, hg, u, smp; fd_hg.divmod(w, wq, hg); FastDiv(ns).divmod(wq, u, smp);
       if (u != cur_u) { q = make_geo<HD, NT>(make_unit(a.s, u), lane, pitch, pitch_o); cur_u = u; }
       const uint32_t sb = smem_addr(sq + (size_t)smp * K * pitch);
       const uint32_t sdb = smem_addr(sdo + (size_t)smp * K * pitch_o);
@@ -430,7 +432,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(a.dqkv + (size_t)n0 * K * 3 * D);
     for (int i = threadIdx.x; i < ns * K * row_vecs; i += blockDim.x) {
-      const int r = i / row_vecs, c = i - r * row_vecs;
+      int r, c; fd_row.divmod(i, r, c);
       dst[i] = *reinterpret_cast<const uint4*>(sdq + (size_t)r * pitch + c * 16);
     }
   }

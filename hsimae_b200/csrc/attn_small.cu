@@ -64,6 +64,7 @@ attn_small_fwd_kernel(AttnArgs a, int spc) {
   const float scale_log2 = rsqrtf((float)HD) * 1.4426950408889634f;
   const int row_vecs = 3 * D / 8, out_vecs = D / 8;
   const int items = a.s.nseq * H;                                        // (sequence, head) pairs of one sample
+  const FastDiv fd_row(row_vecs), fd_out(out_vecs), fd_h(H), fd_items(items);
 
   for (int n0 = blockIdx.x * spc; n0 < a.N; n0 += gridDim.x * spc) {
     const int ns = (a.N - n0) < spc ? (a.N - n0) : spc;
@@ -71,14 +72,14 @@ attn_small_fwd_kernel(AttnArgs a, int spc) {
     const uint4* src = reinterpret_cast<const uint4*>(a.qkv + (size_t)n0 * K * 3 * D);
     const uint32_t sq_addr = smem_addr(sq);
     for (int i = threadIdx.x; i < ns * K * row_vecs; i += blockDim.x) {
-      const int r = i / row_vecs, c = i - r * row_vecs;
+      int r, c; fd_row.divmod(i, r, c);
       cp_async16(sq_addr + (uint32_t)(r * pitch + c * 16), src + i);
     }
     cp_async_wait_all();
     __syncthreads();
     for (int it = threadIdx.x; it < ns * items; it += blockDim.x) {
-      const int smp = it / items, w = it - smp * items;
-      const int seq = w / H, h = w - seq * H;                             // head fastest: a warp reads contiguous 32-byte pieces of a row
+      int smp, w; fd_items.divmod(it, smp, w);
+      int seq, h; fd_h.divmod(w, seq, h);                             // head fastest: a warp reads contiguous 32-byte pieces of a row
       uint8_t* base = sq + (size_t)smp * K * pitch;
       int row[LEN];
 #pragma unroll
@@ -115,7 +116,7 @@ attn_small_fwd_kernel(AttnArgs a, int spc) {
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)n0 * K * D);
     for (int i = threadIdx.x; i < ns * K * out_vecs; i += blockDim.x) {
-      const int r = i / out_vecs, c = i - r * out_vecs;
+      int r, c; fd_out.divmod(i, r, c);
       dst[i] = *reinterpret_cast<const uint4*>(sq + (size_t)r * pitch + c * 16);
     }
     if (a.lse) {
@@ -144,6 +145,7 @@ attn_small_bwd_kernel(AttnArgs a, int spc) {
   const float scale_log2 = scale * 1.4426950408889634f;
   const int row_vecs = 3 * D / 8, o_vecs = D / 8;
   const int items = a.s.nseq * H;
+  const FastDiv fd_row(row_vecs), fd_o(o_vecs), fd_h(H), fd_items(items);
 
   for (int n0 = blockIdx.x * spc; n0 < a.N; n0 += gridDim.x * spc) {
     const int ns = (a.N - n0) < spc ? (a.N - n0) : spc;
@@ -152,13 +154,13 @@ attn_small_bwd_kernel(AttnArgs a, int spc) {
       const uint32_t sq_addr = smem_addr(sq), so_addr = smem_addr(so);
       const uint4* src = reinterpret_cast<const uint4*>(a.qkv + (size_t)n0 * K * 3 * D);
       for (int i = threadIdx.x; i < ns * K * row_vecs; i += blockDim.x) {
-        const int r = i / row_vecs, c = i - r * row_vecs;
+        int r, c; fd_row.divmod(i, r, c);
         cp_async16(sq_addr + (uint32_t)(r * pitch + c * 16), src + i);
       }
       const uint4* src_o = reinterpret_cast<const uint4*>(a.out + (size_t)n0 * K * D);
       const uint4* src_d = reinterpret_cast<const uint4*>(a.dout + (size_t)n0 * K * D);
       for (int i = threadIdx.x; i < ns * K * o_vecs; i += blockDim.x) {
-        const int r = i / o_vecs, c = i - r * o_vecs;
+        int r, c; fd_o.divmod(i, r, c);
         cp_async16(so_addr + (uint32_t)(r * pitch_o + c * 16), src_o + i);
         cp_async16(so_addr + (uint32_t)(r * pitch_o + D * 2 + c * 16), src_d + i);
       }
@@ -168,8 +170,8 @@ attn_small_bwd_kernel(AttnArgs a, int spc) {
     }
     __syncthreads();
     for (int it = threadIdx.x; it < ns * items; it += blockDim.x) {
-      const int smp = it / items, w = it - smp * items;
-      const int seq = w / H, h = w - seq * H;
+      int smp, w; fd_items.divmod(it, smp, w);
+      int seq, h; fd_h.divmod(w, seq, h);
       uint8_t* base = sq + (size_t)smp * K * pitch;
       const uint8_t* obase = so + (size_t)smp * K * pitch_o;
       const float* ls = slse + (size_t)smp * K * H;
@@ -216,7 +218,7 @@ attn_small_bwd_kernel(AttnArgs a, int spc) {
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(a.dqkv + (size_t)n0 * K * 3 * D);
     for (int i = threadIdx.x; i < ns * K * row_vecs; i += blockDim.x) {
-      const int r = i / row_vecs, c = i - r * row_vecs;
+      int r, c; fd_row.divmod(i, r, c);
       dst[i] = *reinterpret_cast<const uint4*>(sq + (size_t)r * pitch + c * 16);
     }
   }

@@ -169,6 +169,15 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
                : "memory");
 }
 
+// x / d and x % d for small runtime divisors in copy loops (x * d < 2^32): one multiply-high instead of the ~20-instruction
+// integer division sequence (those sequences were among the hottest SASS of the attention kernels, profiles/r01g_stall_hotspots.md)
+struct FastDiv {
+  uint32_t inv, d;
+  __device__ __forceinline__ explicit FastDiv(int div) : inv((uint32_t)((0x100000000ull + (uint32_t)div - 1) / (uint32_t)div)), d((uint32_t)div) {}
+  __device__ __forceinline__ int div(int x) const { return d == 1u ? x : (int)__umulhi((uint32_t)x, inv); }   // inv wraps to 0 for d == 1
+  __device__ __forceinline__ void divmod(int x, int& q, int& r) const { q = div(x); r = x - q * (int)d; }
+};
+
 __device__ __forceinline__ float silu_f(float a) { return __fdividef(a, 1.0f + __expf(-a)); }
 
 }  // namespace hsimae
