@@ -35,6 +35,17 @@ class GemmDesc(C.Structure):
     ]
 
 
+class LnBwdDesc(C.Structure):
+    _fields_ = [
+        ("M", c_i32), ("N", c_i32), ("K", c_i32),
+        ("A", c_void_p), ("lda", c_i32), ("B", c_void_p), ("ldb", c_i32),
+        ("x", c_void_p), ("ldx", c_i32), ("stats", c_void_p), ("gamma", c_void_p),
+        ("dx_in", c_void_p), ("ldi", c_i32), ("dx_out", c_void_p), ("ldo", c_i32), ("dxb", c_void_p), ("ldxb", c_i32),
+        ("rowscale", c_void_p), ("rs_mode", c_i32), ("rs_K", c_i32), ("rs_len_l", c_i32), ("rs_G", c_i32),
+        ("dgamma", c_void_p), ("dbeta", c_void_p),
+    ]
+
+
 class MlpDesc(C.Structure):
     _fields_ = [
         ("M", c_i32), ("D", c_i32), ("Hp", c_i32),
@@ -95,6 +106,7 @@ PROTOTYPES = {
     "hsimae_head_forward": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_i32, c_void_p, c_void_p, c_void_p]),
     "hsimae_head_backward": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsimae_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "hsimae_gemm_lnbwd": (c_int, [C.POINTER(LnBwdDesc), c_void_p]),
     "hsimae_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "hsimae_wgrad_group": (c_int, [C.POINTER(WgradDesc), c_i32, c_void_p]),
     "hsimae_mlp_fused": (c_int, [C.POINTER(MlpDesc), c_void_p]),

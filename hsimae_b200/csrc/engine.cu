@@ -493,18 +493,29 @@ int block_backward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int H
   // d(ln2) = dab W13
   a = GemmArgs{};
   a.M = (int)M; a.N = d; a.K = 2 * Hp; a.A = b.dab; a.lda = 2 * Hp; a.B = c.wb + w.w13_t; a.ldb = 2 * Hp;
-  a.out0 = b.dln; a.ld0 = d;
-  HS_TRY(run_gemm(c, a, kEpiBiasBf16));
+  // ... followed by norm2 backward + residual, emitting bf16(rs1 * dx_mid) into its own buffer (dxb is still the dW2 operand):
+  // one kernel where the row fits a tile (kEpiLnBwd), else the dgrad GEMM and ln_bwd_kernel
+  GemmArgs f = a;
+  f.out0 = dx_dst; f.ld0 = d; f.out1 = b.dxb2; f.ld1 = d; f.resid = dx_src; f.ldr = d; f.lnx = s.x_mid; f.ldx = d;
+  f.stats = s.stats2; f.gamma = c.wf + w.g2; f.rs = rs1; f.dgamma = gptr(c, w.n2w); f.dbeta = gptr(c, w.n2b);
+  const bool fuse_ln = !c.p->debug_simt && dx_src != nullptr && gemm_lnbwd_supported(f);
+  if (fuse_ln) {
+    HS_TRY(gemm_tc_lnbwd(f, c.st));
+  } else {
+    a.out0 = b.dln; a.ld0 = d;
+    HS_TRY(run_gemm(c, a, kEpiBiasBf16));
+  }
   WgradArgs& g13 = wj[1];
   g13 = WgradArgs{};
   g13.Mred = (int)M; g13.Nout = 2 * Hp; g13.Kin = d; g13.Y = b.dab; g13.ldy = 2 * Hp; g13.X = s.ln2; g13.ldx = d;
   g13.dst0 = gptr(c, w.w1w); g13.dst1 = gptr(c, w.w3w); g13.ld = d; g13.row_map = 1; g13.rows_valid = H; g13.cols_valid = d;
   g13.bias0 = gptr(c, w.w1b); g13.bias1 = gptr(c, w.w3b);
-  // norm2 backward + residual; emits bf16(rs1 * dx_mid) into its own buffer (dxb is still the dW2 operand)
   LnBwdArgs ln{};
-  ln.M = (int)M; ln.D = d; ln.dy = b.dln; ln.x = s.x_mid; ln.stats = s.stats2; ln.gamma = c.wf + w.g2;
-  ln.dx_in = dx_src; ln.dx_out = dx_dst; ln.dxb = b.dxb2; ln.rs = rs1; ln.dgamma = gptr(c, w.n2w); ln.dbeta = gptr(c, w.n2b);
-  HS_TRY(launch_ln_bwd(ln, c.st));
+  if (!fuse_ln) {
+    ln.M = (int)M; ln.D = d; ln.dy = b.dln; ln.x = s.x_mid; ln.stats = s.stats2; ln.gamma = c.wf + w.g2;
+    ln.dx_in = dx_src; ln.dx_out = dx_dst; ln.dxb = b.dxb2; ln.rs = rs1; ln.dgamma = gptr(c, w.n2w); ln.dbeta = gptr(c, w.n2b);
+    HS_TRY(launch_ln_bwd(ln, c.st));
+  }
   // attention output projection
   a = GemmArgs{};
   a.M = (int)M; a.N = d; a.K = d; a.A = b.dxb2; a.lda = d; a.B = c.wb + w.wproj_t; a.ldb = d; a.out0 = b.dao; a.ld0 = d;
@@ -525,9 +536,15 @@ int block_backward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int H
   HS_TRY(run_wgrad_group(c, wj, 4));
   // q|k|v projection
   a = GemmArgs{};
-  a.M = (int)M; a.N = d; a.K = 3 * d; a.A = b.dqkv; a.lda = 3 * d; a.B = c.wb + w.wqkv_t; a.ldb = 3 * d; a.out0 = b.dln; a.ld0 = d;
+  a.M = (int)M; a.N = d; a.K = 3 * d; a.A = b.dqkv; a.lda = 3 * d; a.B = c.wb + w.wqkv_t; a.ldb = 3 * d;
+  // ... followed by norm1 backward + residual, emitting bf16(rs_prev * dx_in) for the previous block
+  if (fuse_ln) {
+    a.out0 = dx_dst; a.ld0 = d; a.out1 = want_dxb ? b.dxb : nullptr; a.ld1 = d; a.resid = dx_dst; a.ldr = d; a.lnx = x_in; a.ldx = d;
+    a.stats = s.stats1; a.gamma = c.wf + w.g1; a.rs = rs_prev; a.dgamma = gptr(c, w.n1w); a.dbeta = gptr(c, w.n1b);
+    return gemm_tc_lnbwd(a, c.st);
+  }
+  a.out0 = b.dln; a.ld0 = d;
   HS_TRY(run_gemm(c, a, kEpiBiasBf16));
-  // norm1 backward + residual; emits bf16(rs_prev * dx_in) for the previous block
   ln = LnBwdArgs{};
   ln.M = (int)M; ln.D = d; ln.dy = b.dln; ln.x = x_in; ln.stats = s.stats1; ln.gamma = c.wf + w.g1;
   ln.dx_in = dx_dst; ln.dx_out = dx_dst; ln.dxb = want_dxb ? b.dxb : nullptr; ln.rs = rs_prev;
@@ -998,6 +1015,17 @@ int hsimae_gemm(const hsimae_gemm_desc* d, void* stream) {
   a.ln_eps = 1e-5f;
   if (d->impl == 1) return gemm_simt(a, d->epilogue, d->scratch, (cudaStream_t)stream);
   return gemm_tc(a, d->epilogue, (cudaStream_t)stream);
+}
+
+int hsimae_gemm_lnbwd(const hsimae_lnbwd_desc* d, void* stream) {
+  HS_REQUIRE(d != nullptr, "null descriptor");
+  GemmArgs a{};
+  a.M = d->M; a.N = d->N; a.K = d->K; a.A = (const bf16*)d->A; a.lda = d->lda; a.B = (const bf16*)d->B; a.ldb = d->ldb;
+  a.out0 = d->dx_out; a.ld0 = d->ldo; a.out1 = d->dxb; a.ld1 = d->ldxb; a.resid = d->dx_in; a.ldr = d->ldi;
+  a.lnx = d->x; a.ldx = d->ldx; a.stats = const_cast<float*>(d->stats); a.gamma = d->gamma; a.dgamma = d->dgamma; a.dbeta = d->dbeta;
+  a.rs.scale = d->rowscale; a.rs.mode = d->rs_mode; a.rs.K = d->rs_K > 0 ? d->rs_K : 1; a.rs.len_l = d->rs_len_l > 0 ? d->rs_len_l : 1; a.rs.G = d->rs_G;
+  a.ln_eps = 1e-5f;
+  return gemm_tc_lnbwd(a, (cudaStream_t)stream);
 }
 
 int hsimae_mlp_fused(const hsimae_mlp_desc* d, void* stream) {

@@ -20,6 +20,10 @@ enum Epilogue : int {
   kEpiDSwiGLU = 4,   // acc = dg;  out0(bf16, interleaved) = (dg*b*silu'(a) | dg*silu(a)), a,b from `ab`
   kEpiDGate = 5,     // like kEpiDSwiGLU, but a|b = A2 * B2^T + bias is RECOMPUTED by a second GEMM in the same kernel
   kNumEpilogues = 6,
+  // dgrad + LayerNorm backward in one kernel (internal to the engine, tensor-core path only; the tile spans the row):
+  //   dy = acc;  out0(f32) = resid + LN_bwd(dy; lnx, stats, gamma);  out1(bf16, optional) = rs * out0;
+  //   dgamma += sum_rows dy * xhat;  dbeta += sum_rows dy
+  kEpiLnBwd = 6,
 };
 
 struct GemmArgs {
@@ -39,6 +43,9 @@ struct GemmArgs {
   const __nv_bfloat16* A2; int lda2;   // kEpiDGate: [M,K] input of the gated projection
   const __nv_bfloat16* B2; int ldb2;   // kEpiDGate: [2N,K] interleaved w1|w3 (bias = its packed bias)
   float ln_eps;
+  const float* lnx;        int ldx;    // kEpiLnBwd: fp32 [M,N] input of the LayerNorm being differentiated (stats = its mean / rstd)
+  float* dgamma;                       // kEpiLnBwd: [N] accumulated with atomics (nullptr => skipped)
+  float* dbeta;
 };
 
 struct WgradArgs {
@@ -63,6 +70,8 @@ __host__ __device__ inline int packed_col(int which, int h) { return (h / kGate)
 
 int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream);
 int gemm_simt(const GemmArgs& a, int epi, float* scratch, cudaStream_t stream);
+int gemm_tc_lnbwd(const GemmArgs& a, cudaStream_t stream);   // kEpiLnBwd
+bool gemm_lnbwd_supported(const GemmArgs& a);   // shapes the fused dgrad + LayerNorm-backward kernel takes (else: two launches)
 int wgrad_tc(const WgradArgs& a, cudaStream_t stream);
 int wgrad_tc_group(const WgradArgs* jobs, int njobs, cudaStream_t stream);   // up to 4 independent problems in one launch
 int wgrad_simt(const WgradArgs& a, cudaStream_t stream);

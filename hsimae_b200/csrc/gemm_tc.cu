@@ -57,13 +57,15 @@ template <int EPI, int S, int P>
 __global__ void __launch_bounds__(64 + 128 * S, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-               const __grid_constant__ CUtensorMap tmR, GemmArgs p, int block_n, int stages, int n_blks, int num_tiles) {
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmX, GemmArgs p, int block_n, int stages,
+               int n_blks, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   constexpr uint32_t kAccStride = 512 / S;
   constexpr uint32_t kStagingBytes = 4 * S * StagingBufs<EPI, S>::value * kStageBufBytes;
-  constexpr bool kTmaResid = EPI == kEpiResidLN && S == 2;
+  constexpr bool kLnBwd = EPI == kEpiLnBwd;                    // dgrad + LayerNorm backward (S == 2 only)
+  constexpr bool kTmaResid = (EPI == kEpiResidLN || kLnBwd) && S == 2;
 
   const uint32_t b_bytes = (uint32_t)(block_n / P) * 128u;   // this CTA's share of the weight tile
   const uint32_t stage_bytes = kATileBytes + b_bytes;
@@ -74,6 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = tfull + S;
   uint64_t* rbar = tempty + S;                                   // [4 * S][kResidBoxes], only used when kTmaResid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + (kTmaResid ? 4 * S * kResidBoxes : 0));
+  float* gamma_s = reinterpret_cast<float*>(tmem_slot + 4);     // [256] LayerNorm weight (kLnBwd)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,6 +90,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmO0);
     ptx::prefetch_tmap(&tmO1);
     if constexpr (kTmaResid) ptx::prefetch_tmap(&tmR);
+    if constexpr (kLnBwd) ptx::prefetch_tmap(&tmX);
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
     for (int i = 0; i < S; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128 * P); }
     if constexpr (kTmaResid) { for (int i = 0; i < 4 * S * kResidBoxes; ++i) ptx::mbar_init(rbar + i, 1); }
@@ -166,6 +170,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int grp = (warp - 2) >> 2;   // accumulator stage served by this warp's group
     Stager st{ptx::smem_u32(staging) + (uint32_t)(warp - 2) * (StagingBufs<EPI, S>::value * kStageBufBytes), lane, false};
     if constexpr (kTmaResid) { st.tm_resid = &tmR; st.rbar = rbar + (warp - 2) * kResidBoxes; }
+    [[maybe_unused]] LnBwdColAcc col;
+    if constexpr (kLnBwd) {
+      st.tm_x = &tmX;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { col.dg[j] = 0.f; col.db[j] = 0.f; }
+      const int e = (warp - 2) * 32 + lane;                        // 0 .. 128 S - 1
+      for (int i = e; i < 256; i += 128 * S) gamma_s[i] = i < p.N ? p.gamma[i] : 0.f;
+      ptx::named_bar_sync(1, 128 * S);
+    }
     const uint32_t tempty_addr = P == 2 ? ptx::mapa_rank(ptx::smem_u32(tempty + grp), 0) : 0u;
     int it = grp;
     TR_DECL;
@@ -175,12 +188,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       TmemAcc acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * kAccStride};
       const int n0 = n_blk * block_n;
       int width = p.N - n0; if (width > block_n) width = block_n;
-      TR_WAIT(1, tc_epilogue<EPI, (S == 2 ? 1 : 0) | (kTmaResid ? 4 : 0)>(p, acc, st, &tmO0, &tmO1, (m_blk * P + crank) * kBlockM + q * 32, lane, n0, width,
-                       [&]() { TR_WAIT(0, ptx::mbar_wait(tfull + grp, aphase)); ptx::tc_fence_after(); }));
+      auto wait_acc = [&]() { TR_WAIT(0, ptx::mbar_wait(tfull + grp, aphase)); ptx::tc_fence_after(); };
+      if constexpr (kLnBwd) {
+        TR_WAIT(1, tc_lnbwd_epilogue(p, acc, st, &tmO0, &tmO1, (m_blk * P + crank) * kBlockM + q * 32, lane, width, ptx::smem_u32(gamma_s), col, wait_acc));
+      } else {
+        TR_WAIT(1, tc_epilogue<EPI, (S == 2 ? 1 : 0) | (kTmaResid ? 4 : 0)>(p, acc, st, &tmO0, &tmO1, (m_blk * P + crank) * kBlockM + q * 32, lane, n0, width, wait_acc));
+      }
       ptx::tc_fence_before();
       if constexpr (P == 2) ptx::mbar_arrive_cluster(tempty_addr); else ptx::mbar_arrive(tempty + grp);
     }
     st.acquire();   // the staging buffers must outlive every store that reads them
+    if constexpr (kLnBwd) {
+      // gradients of the LayerNorm weight / bias: the warps' column partials meet in the (now idle) staging boxes, one
+      // atomic per column and CTA
+      constexpr uint32_t kWarpStaging = StagingBufs<EPI, S>::value * kStageBufBytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ptx::st_shared_f32(st.base + (uint32_t)((j * 32 + kLnBwdCol(lane)) * 4), col.dg[j]);
+        ptx::st_shared_f32(st.base + 1024u + (uint32_t)((j * 32 + kLnBwdCol(lane)) * 4), col.db[j]);
+      }
+      ptx::named_bar_sync(1, 128 * S);
+      const uint32_t s0 = ptx::smem_u32(staging);
+      for (int e = (warp - 2) * 32 + lane; e < p.N; e += 128 * S) {
+        float g = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4 * S; ++w) {
+          g += ptx::ld_shared_f32(s0 + (uint32_t)w * kWarpStaging + (uint32_t)(e * 4));
+          b += ptx::ld_shared_f32(s0 + (uint32_t)w * kWarpStaging + 1024u + (uint32_t)(e * 4));
+        }
+        if (p.dgamma) atomicAdd(p.dgamma + e, g);
+        if (p.dbeta) atomicAdd(p.dbeta + e, b);
+      }
+    }
     if (warp == 2 && lane == 0) TR_DUMP(2);
   }
 
@@ -1056,15 +1095,15 @@ int launch_gemm_s(const GemmArgs& a, const CUtensorMap* tm, int block_n, int n_b
   // 16-byte loads of one line: leave ~36 KB of the 228 KB shared/L1 array to the cache for them (the two-stage
   // residual epilogue stages its rows through TMA instead)
   const int smem_cap = (EPI == kEpiDSwiGLU || (EPI == kEpiResidLN && S != 2)) ? kSmemMax - 36 * 1024 : kSmemMax;
-  int stages = (smem_cap - staging - 2048) / stage_bytes;
+  int stages = (smem_cap - staging - 2048 - (EPI == kEpiLnBwd ? 1024 : 0)) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > 2 * num_kb) stages = 2 * num_kb;
   if (stages < 2) stages = 2;
-  const size_t smem = (size_t)stages * stage_bytes + staging + 1024 + 512;
+  const size_t smem = (size_t)stages * stage_bytes + staging + 1024 + 512 + (EPI == kEpiLnBwd ? 1024 : 0);
   HS_REQUIRE(smem <= (size_t)kSmemMax, "gemm: tile N=%d needs %zu bytes of shared memory", block_n, smem);
   const int num_tiles = ceil_div(m_blks, P) * n_blks;
   HS_TRY(launch_clustered(gemm_tc_kernel<EPI, S, P>, pair_grid(num_tiles, P), 64 + 128 * S, smem, P, stream, tm[0], tm[1], tm[2],
-                          tm[3], tm[4], a, block_n, stages, n_blks, num_tiles));
+                          tm[3], tm[4], tm[5], a, block_n, stages, n_blks, num_tiles));
   HS_CHECK_LAUNCH("gemm_tc_kernel");
   return kOk;
 }
@@ -1218,10 +1257,11 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   // the 256-column residual epilogue keeps 96 KB of residual boxes: only a pair's half-size weight tiles leave a useful ring
   const bool pair = use_pair(block_n, m_blks, a.K, a.N, ares, epi == kEpiSwiGLU && a.out0 == nullptr) ||
                     ((epi == kEpiResidLN || epi == kEpiBiasBf16) && block_n > 128 && use_pair(block_n, m_blks, 512, a.N, false, false));
-  CUtensorMap tm[5];
+  CUtensorMap tm[6];
   HS_TRY(get_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, kBlockM, &tm[0]));
   HS_TRY(get_tmap(a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(pair ? block_n / 2 : block_n), &tm[1]));
   tm[4] = tm[0];   // residual map: only the residual / LayerNorm epilogue has one
+  tm[5] = tm[0];   // LayerNorm-input map: only gemm_tc_lnbwd has one
   // output boxes: [32 rows x 128 bytes]
   const uint64_t M = (uint64_t)a.M, N = (uint64_t)a.N;
   switch (epi) {
@@ -1251,6 +1291,33 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
   }
   set_error("gemm: bad epilogue %d", epi);
   return kInvalidArgument;
+}
+
+// dgrad + LayerNorm backward in one launch (kEpiLnBwd): 256-column tiles, two accumulator stages, whole rows per tile.
+// HSIMAE_LNBWD_FUSE=0 makes the engine fall back to the dgrad GEMM followed by ln_bwd_vec_kernel (A/B measurements, tests).
+bool gemm_lnbwd_supported(const GemmArgs& a) {
+  static const bool enabled = !(getenv("HSIMAE_LNBWD_FUSE") && atoi(getenv("HSIMAE_LNBWD_FUSE")) == 0);
+  return enabled && a.N > 128 && a.N <= 256 && a.N % 32 == 0 && a.M > 0 && a.K > 0 && a.lda % 8 == 0 && a.ldb % 8 == 0 &&
+         a.ld0 % 4 == 0 && a.ldr % 4 == 0 && a.ldx % 4 == 0 && (a.out1 == nullptr || a.ld1 % 8 == 0);
+}
+
+int gemm_tc_lnbwd(const GemmArgs& a, cudaStream_t stream) {
+  HS_REQUIRE(gemm_lnbwd_supported(a), "gemm(ln-bwd): unsupported shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  HS_REQUIRE(a.A && a.B && a.out0 && a.resid && a.lnx && a.stats && a.gamma, "gemm(ln-bwd): null argument");
+  const int block_n = a.N, n_blks = 1;
+  const int m_blks = ceil_div(a.M, kBlockM);
+  const bool pair = use_pair(block_n, m_blks, 512, a.N, false, false);
+  const uint64_t M = (uint64_t)a.M, N = (uint64_t)a.N;
+  CUtensorMap tm[6];
+  HS_TRY(get_tmap(a.A, (uint64_t)a.K, M, (uint64_t)a.lda, 64, kBlockM, &tm[0]));
+  HS_TRY(get_tmap(a.B, (uint64_t)a.K, N, (uint64_t)a.ldb, 64, (uint32_t)(pair ? block_n / 2 : block_n), &tm[1]));
+  HS_TRY(get_tmap(a.out0, N, M, (uint64_t)a.ld0, 32, 32, &tm[2], 4));
+  if (a.out1) HS_TRY(get_tmap(a.out1, N, M, (uint64_t)a.ld1, 64, 32, &tm[3]));
+  else tm[3] = tm[2];
+  HS_TRY(get_tmap(a.resid, N, M, (uint64_t)a.ldr, 32, 32, &tm[4], 4));
+  HS_TRY(get_tmap(a.lnx, N, M, (uint64_t)a.ldx, 32, 32, &tm[5], 4));
+  return pair ? launch_gemm_s<kEpiLnBwd, 2, 2>(a, tm, block_n, n_blks, m_blks, stream)
+              : launch_gemm_s<kEpiLnBwd, 2, 1>(a, tm, block_n, n_blks, m_blks, stream);
 }
 
 int wgrad_check_args(const WgradArgs& a) {

@@ -85,6 +85,14 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 // ---- CTA-pair (cta_group::2) helpers: two CTAs of a cluster on one TPC drive ONE 256-row MMA; each loads its own
 // 128 A rows and HALF of the B tile, the tensor core reads both shared memories.
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -239,7 +247,8 @@ constexpr int kStageBufBytes = 32 * 128;   // one box
 // with a residual tile by TMA, updated in place and handed back to TMA as the output tile.
 constexpr int kResidBoxes = 3;
 template <int EPI, int S = 4> struct StagingBufs {
-  static constexpr int value = EPI == kEpiSwiGLU ? 2 : (EPI == kEpiResidLN && S == 2 ? kResidBoxes : 1);
+  // the LayerNorm-backward epilogue adds a fourth box for its bf16 output
+  static constexpr int value = EPI == kEpiSwiGLU ? 2 : (EPI == kEpiResidLN && S == 2 ? kResidBoxes : (EPI == kEpiLnBwd ? kResidBoxes + 1 : 1));
 };
 
 struct Stager {
@@ -248,6 +257,7 @@ struct Stager {
   bool pending;      // a committed store may still be reading the buffers
   bool leader = ptx::elect_one();   // the one lane that issues (and later waits for) this warp's bulk stores
   const CUtensorMap* tm_resid = nullptr;   // TMA-staged residual (kEpiResidLN, S == 2): fp32 [M, N], boxes of 32 x 32
+  const CUtensorMap* tm_x = nullptr;       // kEpiLnBwd: the LayerNorm input, same box shape
   uint64_t* rbar = nullptr;                // this warp's kResidBoxes "residual box filled" barriers
   uint32_t rphase = 0;                     // their phase bits
   // wait until the TMA unit has finished reading every box this warp handed over
@@ -425,14 +435,16 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
         acc.template load<32>(c, v);
         ptx::mbar_wait(st.rbar + b, (st.rphase >> b) & 1u);
         st.rphase ^= 1u << b;
+        uint4 rr[8];   // all eight loads first: the volatile accessors keep program order, one exposed latency instead of eight
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rr[j] = ptx::ld_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4));
         if (p.bias) add_vec<32>(p.bias + c, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint4 r = ptx::ld_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4));
-          v[4 * j] = fmaf(s, v[4 * j], __uint_as_float(r.x));
-          v[4 * j + 1] = fmaf(s, v[4 * j + 1], __uint_as_float(r.y));
-          v[4 * j + 2] = fmaf(s, v[4 * j + 2], __uint_as_float(r.z));
-          v[4 * j + 3] = fmaf(s, v[4 * j + 3], __uint_as_float(r.w));
+          v[4 * j] = fmaf(s, v[4 * j], __uint_as_float(rr[j].x));
+          v[4 * j + 1] = fmaf(s, v[4 * j + 1], __uint_as_float(rr[j].y));
+          v[4 * j + 2] = fmaf(s, v[4 * j + 2], __uint_as_float(rr[j].z));
+          v[4 * j + 3] = fmaf(s, v[4 * j + 3], __uint_as_float(rr[j].w));
         }
         if (p.resid2 && valid) {
           float r2[32];
@@ -528,6 +540,176 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
       for (c = 0; c + 32 <= width; c += 32) pass3(std::integral_constant<int, 32>{}, c);
       for (; c + 16 <= width; c += 16) pass3(std::integral_constant<int, 16>{}, c);
       if (valid && p.stats) *reinterpret_cast<float2*>(p.stats + 2 * (size_t)m) = make_float2(mean, rstd);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dgrad + LayerNorm backward (kEpiLnBwd).  The accumulator row of a thread is dy, the gradient w.r.t. the LayerNorm
+// output; the tile spans the whole row.  Two passes over the accumulator, sixteen 32-column steps, three fp32 boxes per
+// warp rotating through the copy engine two steps ahead of their use:
+//   pass A (steps 0..7):  box = LayerNorm input x.  xhat = (x - mean) rstd, t = dy gamma; row sums s1 = sum t,
+//                         s2 = sum t xhat; column sums of dy xhat and dy (gradients of gamma / beta) by a butterfly
+//                         exchange across the warp's 32 rows, kept in registers across tiles; (t, xhat) go back into the
+//                         accumulator packed as a bf16 pair (the separate kernel read dy as bf16 too).
+//   pass B (steps 8..15): box = incoming residual gradient; dx = rstd (t - s1/N - xhat s2/N) + dx_in written in place
+//                         and handed back to TMA as the outgoing residual gradient; bf16(rs dx) -- the next dgrad's
+//                         operand -- through the fourth box, 64 columns per store.
+// Reference: the autograd of nn.LayerNorm at /root/reference/Models.py:304-305 (norm1 / norm2 of Block.forward).
+// ---------------------------------------------------------------------------
+// Column sums over the warp's 32 rows of a [32 rows x 32 fp32] box (128B-swizzled rows: 16-byte piece j of row r sits at
+// piece j ^ (r & 7)).  Lane l reads piece (l & 7) of the eight rows r = (l >> 3) + 4 i -- every quarter warp reads one whole
+// 128-byte row, no bank conflicts -- two butterfly steps join the four row groups, and the lane keeps column
+// 4 (l & 7) + (l >> 3) of the chunk (kLnBwdCol).  A shuffle-only transposed reduction of the register rows (31 shuffles
+// and 62 selects per quantity) measured 875 cycles per call here; this one is eight loads deep.
+__device__ __forceinline__ float box_colsum(uint32_t box, int lane) {
+  const int p = lane & 7, g = lane >> 3;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  uint4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = g + 4 * i;
+    v[i] = ptx::ld_shared_v4(box + (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a0 += __uint_as_float(v[i].x); a1 += __uint_as_float(v[i].y); a2 += __uint_as_float(v[i].z); a3 += __uint_as_float(v[i].w);
+  }
+#pragma unroll
+  for (int h = 8; h <= 16; h <<= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, h); a1 += __shfl_xor_sync(0xffffffffu, a1, h);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, h); a3 += __shfl_xor_sync(0xffffffffu, a3, h);
+  }
+  return g == 0 ? a0 : (g == 1 ? a1 : (g == 2 ? a2 : a3));
+}
+__device__ __forceinline__ int kLnBwdCol(int lane) { return 4 * (lane & 7) + (lane >> 3); }   // column (within its chunk) a lane accumulates
+
+struct LnBwdColAcc { float dg[8], db[8]; };   // column 32 * j + kLnBwdCol(lane)
+
+template <class Wait>
+__device__ __forceinline__ void tc_lnbwd_epilogue(const GemmArgs& p, TmemAcc& acc, Stager& st, const CUtensorMap* tmO0,
+                                                  const CUtensorMap* tmO1, int m0, int lane, int width, uint32_t gamma_smem,
+                                                  LnBwdColAcc& col, Wait wait_acc) {
+  const int m = m0 + lane;
+  const bool valid = m < p.M;
+  const int nch = width >> 5;            // <= 8
+  const int nsteps = 2 * nch;
+  float mean = 0.f, rstd = 0.f, rsc = 1.f;
+  if (valid) {
+    const float2 ms = *reinterpret_cast<const float2*>(p.stats + 2 * (size_t)m);
+    mean = ms.x; rstd = ms.y;
+    rsc = row_scale(p.rs, m);
+  }
+  auto issue = [&](int k) {
+    if (st.leader) {
+      const int b = k % kResidBoxes;
+      ptx::mbar_expect_tx(st.rbar + b, kStageBufBytes);
+      if (k < nch) ptx::tma_load_2d_addr(st.base + (uint32_t)b * kStageBufBytes, st.tm_x, st.rbar + b, k * 32, m0);
+      else ptx::tma_load_2d_addr(st.base + (uint32_t)b * kStageBufBytes, st.tm_resid, st.rbar + b, (k - nch) * 32, m0);
+    }
+  };
+  st.acquire();                    // every box is free again (stores of the previous tile have been read)
+  issue(0);
+  issue(1);
+  wait_acc();
+  float s1 = 0.f, s2 = 0.f;
+  const uint32_t box_b = st.base + (uint32_t)kResidBoxes * kStageBufBytes + (uint32_t)lane * 128u;   // this lane's row of the fourth box
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {   // unrolled: the column accumulators are registers
+    if (ch >= nch) break;
+    const int b = ch % kResidBoxes, c = ch * 32;
+    const uint32_t row = st.base + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u;
+    float dy[32], pg[32];
+    acc.template load<32>(c, dy);
+    ptx::mbar_wait(st.rbar + b, (st.rphase >> b) & 1u);
+    st.rphase ^= 1u << b;
+    uint4 xr[8], gr[8];            // all loads first: the volatile accessors keep program order
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xr[j] = ptx::ld_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gr[j] = ptx::ld_shared_v4(gamma_smem + (uint32_t)((c + 4 * j) * 4));
+    float wf[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xs[4] = {__uint_as_float(xr[j].x), __uint_as_float(xr[j].y), __uint_as_float(xr[j].z), __uint_as_float(xr[j].w)};
+      const float gs[4] = {__uint_as_float(gr[j].x), __uint_as_float(gr[j].y), __uint_as_float(gr[j].z), __uint_as_float(gr[j].w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        const float xh = (xs[e] - mean) * rstd;
+        const float t = dy[i] * gs[e];
+        s1 += t;
+        s2 = fmaf(t, xh, s2);
+        pg[i] = dy[i] * xh;
+        wf[i] = __uint_as_float(pack_bf16x2(t, xh));
+      }
+    }
+    acc.template store<32>(c, wf);
+    // gradients of gamma / beta: dy * xhat goes into the x box (dead now), dy into the bf16 box (idle in this pass)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ptx::st_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4), pack4_f32(pg + 4 * j));
+      ptx::st_shared_v4(box_b + (uint32_t)((j ^ (lane & 7)) << 4), pack4_f32(dy + 4 * j));
+    }
+    __syncwarp();
+    col.dg[ch] += box_colsum(st.base + (uint32_t)b * kStageBufBytes, lane);
+    col.db[ch] += box_colsum(st.base + (uint32_t)kResidBoxes * kStageBufBytes, lane);
+    ptx::fence_proxy_async();      // the x box was written through the generic proxy; the copy engine refills it next
+    __syncwarp();                  // every lane has read both boxes: they may be rewritten / refilled
+    issue(ch + 2);                 // box (ch + 2) % 3 was last read one chunk ago; nsteps >= ch + 3 always (pass B follows)
+  }
+  acc.fence_store();
+  const float inv = 1.0f / (float)width;
+  const float a1 = s1 * inv, a2 = s2 * inv;
+  const bool want_b = p.out1 != nullptr;
+#pragma unroll 1
+  for (int ch = 0; ch < nch; ++ch) {
+    const int k = nch + ch;
+    const int b = k % kResidBoxes, c = ch * 32;
+    const uint32_t row = st.base + (uint32_t)b * kStageBufBytes + (uint32_t)lane * 128u;
+    float wf[32], v[32];
+    acc.template load<32>(c, wf);
+    ptx::mbar_wait(st.rbar + b, (st.rphase >> b) & 1u);
+    st.rphase ^= 1u << b;
+    uint4 dr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dr[j] = ptx::ld_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ds[4] = {__uint_as_float(dr[j].x), __uint_as_float(dr[j].y), __uint_as_float(dr[j].z), __uint_as_float(dr[j].w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        const float2 tx = unpack_bf16x2(__float_as_uint(wf[i]));   // (t, xhat)
+        v[i] = fmaf(rstd, tx.x - a1 - tx.y * a2, ds[e]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ptx::st_shared_v4(row + (uint32_t)((j ^ (lane & 7)) << 4), pack4_f32(v + 4 * j));
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (st.leader) {
+      ptx::tma_store_2d(tmO0, st.base + (uint32_t)b * kStageBufBytes, c, m0);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read1();   // everything but the store just issued has been read: box (k + 2) % 3 and the bf16 box are free
+    }
+    __syncwarp();
+    st.pending = true;
+    if (k + 2 < nsteps) issue(k + 2);
+    if (want_b) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= rsc;
+      const int j0 = (ch & 1) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ptx::st_shared_v4(box_b + (uint32_t)(((j0 + i) ^ (lane & 7)) << 4), pack8_bf16(v + 8 * i));
+      if ((ch & 1) || ch + 1 == nch) {
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (st.leader) {
+          ptx::tma_store_2d(tmO1, st.base + (uint32_t)kResidBoxes * kStageBufBytes, c & ~63, m0);
+          ptx::bulk_commit();
+        }
+      }
     }
   }
 }

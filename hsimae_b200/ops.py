@@ -80,6 +80,32 @@ def gemm(A, B, epilogue, *, impl=IMPL_TC, bias=None, resid=None, resid2=None, ga
     return out
 
 
+def gemm_lnbwd(A, B, x, stats, gamma, dx_in, *, want_dxb=True, rowscale=None, rs_mode=0, rs_K=1, rs_len_l=1, rs_G=1,
+               dgamma=None, dbeta=None, inplace=False):
+    """dy = A[M,K] @ B[N,K]^T followed by the LayerNorm backward of `x` (row statistics `stats` = (mean, rstd), weight `gamma`)
+    in one launch: returns dx = dx_in + LN_bwd(dy), bf16(rowscale * dx) and the accumulated dgamma / dbeta."""
+    _need_cuda(A, B)
+    L = _lib.load()
+    M, K = A.shape
+    N = B.shape[0]
+    dev = A.device
+    d = _lib.LnBwdDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.B, d.ldb = _p(A), A.stride(0), _p(B), B.stride(0)
+    d.x, d.ldx, d.stats, d.gamma = _p(x), x.stride(0), _p(stats), _p(gamma)
+    out = {"dx": dx_in if inplace else torch.empty(M, N, dtype=torch.float32, device=dev)}
+    d.dx_in, d.ldi, d.dx_out, d.ldo = _p(dx_in), dx_in.stride(0), _p(out["dx"]), N
+    if want_dxb:
+        out["dxb"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        d.dxb, d.ldxb = _p(out["dxb"]), N
+    out["dgamma"] = dgamma if dgamma is not None else torch.zeros(N, dtype=torch.float32, device=dev)
+    out["dbeta"] = dbeta if dbeta is not None else torch.zeros(N, dtype=torch.float32, device=dev)
+    d.dgamma, d.dbeta = _p(out["dgamma"]), _p(out["dbeta"])
+    d.rowscale, d.rs_mode, d.rs_K, d.rs_len_l, d.rs_G = _p(rowscale), rs_mode, rs_K, rs_len_l, rs_G
+    _lib.check(L.hsimae_gemm_lnbwd(C.byref(d), _stream()), "gemm_lnbwd")
+    return out
+
+
 def mlp_fused(X, W13, b13, W2, b2, resid, *, gamma=None, beta=None, resid2=None, keep_g=True,
               rowscale=None, rs_mode=0, rs_K=1, rs_len_l=1, rs_G=1):
     """out = resid + rs * (W2 (silu(W1 x) * W3 x) + b2) [+ resid2], LayerNorm of the result -- one kernel (csrc/block_fused.cu).

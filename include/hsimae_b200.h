@@ -151,6 +151,26 @@ typedef struct hsimae_gemm_desc {
 } hsimae_gemm_desc;
 int hsimae_gemm(const hsimae_gemm_desc* d, void* stream);
 
+/* dgrad GEMM + LayerNorm backward in ONE launch (csrc/gemm.cuh kEpiLnBwd; replaces the autograd of nn.LayerNorm behind
+ * Models.py:304-305 together with the nn.Linear input gradient that feeds it):
+ *   dy = A[M,K] * B[N,K]^T;  dx_out = dx_in + LN_bwd(dy; x, stats = (mean, rstd) per row, gamma);
+ *   dxb (optional) = bf16(rowscale * dx_out);  dgamma += sum_rows dy * xhat;  dbeta += sum_rows dy.
+ * 128 < N <= 256, N % 32 == 0 (the row has to fit one accumulator tile); dx_in == dx_out is allowed. */
+typedef struct hsimae_lnbwd_desc {
+  int32_t M, N, K;
+  const void* A; int32_t lda;
+  const void* B; int32_t ldb;
+  const float* x; int32_t ldx;
+  const float* stats;
+  const float* gamma;
+  const float* dx_in; int32_t ldi;
+  float* dx_out; int32_t ldo;
+  void* dxb; int32_t ldxb;
+  const float* rowscale; int32_t rs_mode, rs_K, rs_len_l, rs_G;
+  float* dgamma; float* dbeta;
+} hsimae_lnbwd_desc;
+int hsimae_gemm_lnbwd(const hsimae_lnbwd_desc* d, void* stream);
+
 /* Programmatic dependent launch of the library's kernels on (default, HSIMAE_PDL=0 disables) / off; returns the previous
  * setting.  Off is for per-kernel timing: overlapped prologues make consecutive kernels' profiler durations overlap. */
 int hsimae_set_pdl(int on);

@@ -139,6 +139,43 @@ def test_gemm_resid_layernorm(ops, M, N, K, variant):
             assert torch.allclose(out["stats"][:, 1], (var + 1e-5).rsqrt(), rtol=1e-4)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 768), (300, 256, 1376), (129, 192, 576), (40000, 256, 768), (77, 160, 64)])
+@pytest.mark.parametrize("variant", ["plain", "inplace+scale", "no_dxb"])
+def test_gemm_lnbwd(ops, M, N, K, variant):
+    """dgrad GEMM + LayerNorm backward in one launch (kEpiLnBwd) vs torch autograd of F.layer_norm in fp32 on the same
+    bf16 operands.  Inside the kernel (t, xhat) make one round trip through a bf16 pair: tolerance = bf16 rounding."""
+    A, B = _rand_bf16(M, K, seed=15), _rand_bf16(N, K, scale=0.05, seed=16)
+    x = (3.0 * torch.randn(M, N, device=DEV) + torch.randn(M, 1, device=DEV)).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(N, device=DEV)).requires_grad_(True)
+    beta = torch.zeros(N, device=DEV, requires_grad=True)
+    dx_in = torch.randn(M, N, device=DEV)
+    dy = A.float() @ B.float().t()
+    F.layer_norm(x, (N,), gamma, beta, 1e-5).backward(dy)
+    xd = x.detach()
+    mean, var = xd.mean(1), xd.var(1, unbiased=False)
+    stats = torch.stack([mean, (var + 1e-5).rsqrt()], 1).contiguous()
+    ref_dx = dx_in + x.grad
+    kw = {}
+    s = None
+    if variant == "inplace+scale":
+        Ktok, ll, G = 6, 3, 2
+        Mpad = (M + Ktok - 1) // Ktok
+        scale = (torch.rand(Mpad * G, device=DEV) > 0.3).float() / 0.7
+        rows = torch.arange(M, device=DEV)
+        s = scale[(rows // Ktok) * G + (rows % Ktok) // ll]
+        kw.update(rowscale=scale, rs_mode=1, rs_K=Ktok, rs_len_l=ll, rs_G=G, inplace=True)
+    if variant == "no_dxb":
+        kw.update(want_dxb=False)
+    dg0, db0 = torch.randn(N, device=DEV), torch.randn(N, device=DEV)      # the gradients accumulate
+    out = ops.gemm_lnbwd(A, B, xd, stats, gamma.detach(), dx_in.clone(), dgamma=dg0.clone(), dbeta=db0.clone(), **kw)
+    assert rel_err(out["dx"], ref_dx) < TOL_BF16
+    if variant != "no_dxb":
+        ref_b = ref_dx * s[:, None] if s is not None else ref_dx
+        assert rel_err(out["dxb"].float(), ref_b) < 2 * TOL_BF16
+    assert rel_err(out["dgamma"] - dg0, gamma.grad) < 1e-3
+    assert rel_err(out["dbeta"] - db0, beta.grad) < 1e-3
+
+
 @pytest.mark.parametrize("M,d,H", [(1000, 256, 684), (300, 64, 172), (129, 128, 344), (50, 144, 384)])
 def test_gemm_swiglu_fwd_bwd(ops, M, d, H):
     hp = (H + 15) // 16 * 16

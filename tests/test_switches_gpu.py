@@ -22,6 +22,7 @@ COMBOS = [
     {"HSIMAE_FUSED_MLP_PAIR": "0"},
     {"HSIMAE_FUSED_MLP": "0", "HSIMAE_EMBED_MMA": "0"},
     {"HSIMAE_RECOMPUTE_MIN_ROWS": "8192"},
+    {"HSIMAE_LNBWD_FUSE": "0"},                                  # dgrad GEMM and LayerNorm backward as two launches
     {"HSIMAE_WGRAD_GROUP": "0", "HSIMAE_OVERLAP": "0"},          # ... and both encoder chains on one stream                                 # one weight-gradient launch per problem
 ]
 
