@@ -201,8 +201,9 @@ def ncu_traffic(cand: str):
     `ncu --set full` capture (profiles/r01e_ncu_full_kernels.json, written by tools/ncu_summary.py from a
     tools/prof_kernels.py run at the shapes timed here), or None"""
     want = {"gemm_tc_dgate_kernel": "d(gate)", "mlp_fused_kernel": "fused gated MLP", "gemm_tc_kernel<Bias> qkv": "qkv projection",
-            "wgrad_tc_kernel dW13": "wgrad dW13", "gemm_tc_kernel<Bias> dgrad": "dgrad K=1376"}
-    for name in ("r02_ncu_full_kernels.json", "r01e_ncu_full_kernels.json"):
+            "wgrad_group_kernel": "wgrad group", "gemm_tc_kernel<LnBwd> dgrad [M,1376]": "dgrad K=1376 + LN bwd",
+            "gemm_tc_kernel<LnBwd> dgrad [M,768]": "dgrad K=768 + LN bwd"}
+    for name in ("r02i_ncu_full_kernels.json", "r02_ncu_full_kernels.json", "r01e_ncu_full_kernels.json"):
         try:
             rows = json.load(open(os.path.join(ROOT, "profiles", name)))
             for key, label in want.items():
@@ -230,6 +231,15 @@ def dominant_kernel_roofline(batch: int, pk):
     gw13 = torch.zeros(684, D, device=dev); gw13b = torch.zeros(684, D, device=dev)
     per_step = 21   # encoder blocks per direction
     x2 = bf(M, D)          # the d(gate) call reads TWO distinct activations (dy and the LayerNorm-2 output)
+    w13t_full, wqkv_t, dqkv = bf(D, 2 * H) * 0.05, bf(D, 3 * D) * 0.05, bf(M, 3 * D)
+    xf, dxf = torch.randn(M, D, device=dev), torch.randn(M, D, device=dev)
+    stats = torch.stack([xf.mean(1), (xf.var(1, unbiased=False) + 1e-5).rsqrt()], 1).contiguous()
+    dgam, dbet = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    z = lambda *s_: torch.zeros(*s_, device=dev)
+    wg_jobs = [dict(Y=x, X=g, dst0=z(D, 684), cols_valid=684, bias0=z(D)),
+               dict(Y=dab, X=x2, dst0=gw13, dst1=gw13b, row_map=1, rows_valid=684, bias0=z(684), bias1=z(684)),
+               dict(Y=x, X=x2, dst0=z(D, D), bias0=z(D)),
+               dict(Y=dqkv, X=x2, dst0=z(3 * D, D), bias0=z(3 * D))]
     b13, b2 = torch.zeros(2 * H, device=dev), torch.zeros(D, device=dev)
     # name -> (launch, ALGORITHMIC flops per SURVEY 8(d) accounting, algorithmic bytes, launches per step, EXECUTED flops)
     cands = {
@@ -241,10 +251,15 @@ def dominant_kernel_roofline(batch: int, pk):
             2 * M * D + 4 * M * D + 2 * 3 * H * D + 2 * M * H + 4 * M * D + 2 * M * D, per_step, 2 * M * 3 * H * D),
         "gemm_tc_kernel<Bias> qkv [M,256]x[256,768]": (lambda: ops.gemm(x, wqkv, ops.EPI_BIAS_BF16), 2 * M * 3 * D * D,
                                                             2 * (M * D + 3 * D * D + M * 3 * D), per_step, 2 * M * 3 * D * D),
-        "wgrad_tc_kernel dW13 [1376,M]x[M,256]": (lambda: ops.wgrad(dab, x, gw13, dst1=gw13b, row_map=1, rows_valid=684),
-                                                  2 * M * 2 * H * D, 2 * (M * 2 * H + M * D) + 4 * 2 * 684 * D, per_step, 2 * M * 2 * H * D),
-        "gemm_tc_kernel<Bias> dgrad [M,1376]x[1376,256]": (lambda: ops.gemm(dab, w13.t().contiguous(), ops.EPI_BIAS_BF16),
-                                                           2 * M * 2 * H * D, 2 * (M * 2 * H + 2 * H * D + M * D), per_step, 2 * M * 2 * H * D),
+        "wgrad_group_kernel dW2 | dW1,dW3 | dWproj | dWq,k,v of one block (reduction over M)": (
+            lambda: ops.wgrad_group(wg_jobs), 2 * M * D * (H + 2 * H + D + 3 * D), 2 * M * (D + H + 2 * H + D + D + D + 3 * D + D), per_step,
+            2 * M * D * (H + 2 * H + D + 3 * D)),
+        "gemm_tc_kernel<LnBwd> dgrad [M,1376]x[1376,256] + LayerNorm backward + residual gradient": (
+            lambda: ops.gemm_lnbwd(dab, w13t_full, xf, stats, gamma, dxf, dgamma=dgam, dbeta=dbet, inplace=True),
+            2 * M * 2 * H * D, 2 * (M * 2 * H + 2 * H * D) + M * D * (4 + 4 + 4 + 2), per_step, 2 * M * 2 * H * D),
+        "gemm_tc_kernel<LnBwd> dgrad [M,768]x[768,256] + LayerNorm backward + residual gradient": (
+            lambda: ops.gemm_lnbwd(dqkv, wqkv_t, xf, stats, gamma, dxf, dgamma=dgam, dbeta=dbet, inplace=True),
+            2 * M * 3 * D * D, 2 * (M * 3 * D + 3 * D * D) + M * D * (4 + 4 + 4 + 2), per_step, 2 * M * 3 * D * D),
     }
     rows = {}
     for name, (fn, flops, nbytes, count, executed) in cands.items():
@@ -300,7 +315,7 @@ def step_kernel_accounting(step_fn, batch: int, pk):
     for e in evs:
         a = agg.setdefault(e.name, [0, 0.0])
         a[0] += 1; a[1] += e.device_time   # us
-    fam = {"gemm": ("gemm_tc", "mlp_fused", "wgrad_"), "attention": ("attn_",), "ln_bwd": ("ln_bwd",), "embed": ("embed_",),
+    fam = {"gemm+ln_bwd (fused)": ("gemm_tc_kernel<6,",), "gemm": ("gemm_tc", "mlp_fused", "wgrad_"), "attention": ("attn_",), "ln_bwd": ("ln_bwd",), "embed": ("embed_",),
            "loss": ("loss_kernel",), "fill": ("fill_",), "mask": ("mask_kernel",), "pack": ("pack_kernel",), "nccl": ("nccl",)}
     fams = {k: [0, 0.0] for k in fam}; fams["other (optimizer, rand, casts)"] = [0, 0.0]
     for name, (n, us) in agg.items():
@@ -310,7 +325,10 @@ def step_kernel_accounting(step_fn, batch: int, pk):
         else:
             fams["other (optimizer, rand, casts)"][0] += n; fams["other (optimizer, rand, casts)"][1] += us
     total = sum(v[1] for v in fams.values())
-    g_us = fams["gemm"][1]
+    g_pure_us, nfused = fams["gemm"][1], fams["gemm+ln_bwd (fused)"][0]
+    g_us = g_pure_us + fams["gemm+ln_bwd (fused)"][1]
+    # the fused dgrad + LayerNorm-backward launches (21 encoder blocks x 2 at Large): their GEMM FLOPs, for the fraction without them
+    fused_flop = nfused * 2.0 * (batch * 18) * 256 * (2 * 688 + 3 * 256) / 2
     out = {"kernel_time_sum_ms": total / 1e3, "launches": sum(v[0] for v in fams.values()),
            "families": {k: {"launches": v[0], "ms": v[1] / 1e3, "share": v[1] / total} for k, v in fams.items() if v[0]},
            "note": "one untimed step in plain stream order (programmatic dependent launch off) under the CUPTI activity profiler",
@@ -318,7 +336,10 @@ def step_kernel_accounting(step_fn, batch: int, pk):
                                 "achieved_tflops": batch * GEMM_FLOP_PER_PATCH / (g_us * 1e-6) / 1e12, "peak_tflops": pk["tf_sus"],
                                 "frac": batch * GEMM_FLOP_PER_PATCH / (g_us * 1e-6) / 1e12 / pk["tf_sus"], "peak": "sustained, " + pk["src"],
                                 "frac_of_burst": batch * GEMM_FLOP_PER_PATCH / (g_us * 1e-6) / 1e12 / pk["tf"],
-                                "note": "GEMM + weight-gradient kernels only (tcgen05): algorithmic FLOPs, recomputation not counted"}}
+                                "frac_excl_fused_ln": (batch * GEMM_FLOP_PER_PATCH - fused_flop) / (g_pure_us * 1e-6) / 1e12 / pk["tf_sus"],
+                                "note": "GEMM + weight-gradient kernels only (tcgen05): algorithmic FLOPs, recomputation not counted; the "
+                                        "dgrad kernels that also do the LayerNorm backward (HBM-bound work of the former ln_bwd family) are "
+                                        "inside `frac` and left out of `frac_excl_fused_ln`"}}
     # HBM-bound kernels: algorithmic bytes per launch (every operand / result once), Large, mask 0.5
     B, K, P, D, Dd, PK = batch, 18, 36, 256, 64, 72
     M, Md = B * K, B * P

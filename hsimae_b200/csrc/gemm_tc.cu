@@ -1297,7 +1297,8 @@ int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream) {
 // HSIMAE_LNBWD_FUSE=0 makes the engine fall back to the dgrad GEMM followed by ln_bwd_vec_kernel (A/B measurements, tests).
 bool gemm_lnbwd_supported(const GemmArgs& a) {
   static const bool enabled = !(getenv("HSIMAE_LNBWD_FUSE") && atoi(getenv("HSIMAE_LNBWD_FUSE")) == 0);
-  return enabled && a.N > 128 && a.N <= 256 && a.N % 32 == 0 && a.M > 0 && a.K > 0 && a.lda % 8 == 0 && a.ldb % 8 == 0 &&
+  static const int min_n = getenv("HSIMAE_LNBWD_MIN_N") ? atoi(getenv("HSIMAE_LNBWD_MIN_N")) : 32;
+  return enabled && a.N >= min_n && a.N >= 32 && a.N <= 256 && a.N % 32 == 0 && a.M > 0 && a.K > 0 && a.lda % 8 == 0 && a.ldb % 8 == 0 &&
          a.ld0 % 4 == 0 && a.ldr % 4 == 0 && a.ldx % 4 == 0 && (a.out1 == nullptr || a.ld1 % 8 == 0);
 }
 

@@ -610,7 +610,7 @@ __device__ __forceinline__ void tc_lnbwd_epilogue(const GemmArgs& p, TmemAcc& ac
   };
   st.acquire();                    // every box is free again (stores of the previous tile have been read)
   issue(0);
-  issue(1);
+  issue(1);                        // nsteps >= 2
   wait_acc();
   float s1 = 0.f, s2 = 0.f;
   const uint32_t box_b = st.base + (uint32_t)kResidBoxes * kStageBufBytes + (uint32_t)lane * 128u;   // this lane's row of the fourth box
@@ -656,7 +656,7 @@ __device__ __forceinline__ void tc_lnbwd_epilogue(const GemmArgs& p, TmemAcc& ac
     col.db[ch] += box_colsum(st.base + (uint32_t)kResidBoxes * kStageBufBytes, lane);
     ptx::fence_proxy_async();      // the x box was written through the generic proxy; the copy engine refills it next
     __syncwarp();                  // every lane has read both boxes: they may be rewritten / refilled
-    issue(ch + 2);                 // box (ch + 2) % 3 was last read one chunk ago; nsteps >= ch + 3 always (pass B follows)
+    if (ch + 2 < nsteps) issue(ch + 2);   // box (ch + 2) % 3 was last read one chunk ago
   }
   acc.fence_store();
   const float inv = 1.0f / (float)width;

@@ -7,7 +7,8 @@ import csv, io, json, subprocess, sys
 LABELS = ["qkv projection (streaming pair kernel, bias)", "gated up-projection, g only (A-resident, SwiGLU)", "down-projection + residual + LayerNorm (TMA-staged residual)",
           "d(gate) with recomputed a|b (dual GEMM)", "dgrad K=1376 (pair)", "wgrad dW13 (pair)", "wgrad dW2",
           "attention fwd fusion (len 18)", "attention bwd fusion (len 18)", "attention fwd spatial", "attention fwd spectral",
-          "fused gated MLP, training (g kept)", "fused gated MLP, inference"]
+          "fused gated MLP, training (g kept)", "fused gated MLP, inference",
+          "dgrad K=1376 + LN bwd (kEpiLnBwd)", "dgrad K=768 + LN bwd (kEpiLnBwd)", "wgrad group (dW2 | dW13 | dWproj | dWqkv)"]
 
 
 def main(rep, out):

@@ -19,6 +19,15 @@ w2t = bf(H, D) * 0.05
 x2 = bf(M, D)
 b13, b2 = torch.zeros(2 * H, device=dev), torch.zeros(D, device=dev)
 w13t = bf(D, 2 * H) * 0.05
+wqkvt = bf(D, 3 * D) * 0.05
+xf, dxf = torch.randn(M, D, device=dev), torch.randn(M, D, device=dev)
+stats = torch.stack([xf.mean(1), (xf.var(1, unbiased=False) + 1e-5).rsqrt()], 1).contiguous()
+dgam, dbet = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+z = lambda *s_: torch.zeros(*s_, device=dev)
+wg_jobs = [dict(Y=x, X=g, dst0=z(D, 684), cols_valid=684, bias0=z(D)),
+           dict(Y=dab, X=x2, dst0=gw1, dst1=gw3, row_map=1, rows_valid=684, bias0=gb1, bias1=gb3),
+           dict(Y=x, X=x2, dst0=z(D, D), bias0=z(D)),
+           dict(Y=dqkv, X=x2, dst0=z(3 * D, D), bias0=z(3 * D))]
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 for _ in range(reps):
     torch.cuda.profiler.start()
@@ -35,6 +44,9 @@ for _ in range(reps):
     out, lse = ops.attention_forward(qkv, B, D, 16, 18, 6, 3, 1, 6)          # spectral
     ops.mlp_fused(x, w13, b13, w2, b2, resid, gamma=gamma, beta=beta)         # fused gated MLP (training: g kept)
     ops.mlp_fused(x, w13, b13, w2, b2, resid, gamma=gamma, beta=beta, keep_g=False)   # fused gated MLP (inference)
+    ops.gemm_lnbwd(dab, w13t, xf, stats, gamma, dxf, dgamma=dgam, dbeta=dbet, inplace=True)    # dgrad K=1376 + LayerNorm backward
+    ops.gemm_lnbwd(dqkv, wqkvt, xf, stats, gamma, dxf, dgamma=dgam, dbeta=dbet, inplace=True)  # dgrad K=768 + LayerNorm backward
+    ops.wgrad_group(wg_jobs)                                                                   # the four weight gradients of a block
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 print("done")
