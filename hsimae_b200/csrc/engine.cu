@@ -498,7 +498,7 @@ int block_backward(const Ctx& c, const BlockW& w, int64_t M, int N, int d, int H
   GemmArgs f = a;
   f.out0 = dx_dst; f.ld0 = d; f.out1 = b.dxb2; f.ld1 = d; f.resid = dx_src; f.ldr = d; f.lnx = s.x_mid; f.ldx = d;
   f.stats = s.stats2; f.gamma = c.wf + w.g2; f.rs = rs1; f.dgamma = gptr(c, w.n2w); f.dbeta = gptr(c, w.n2b);
-  const bool fuse_ln = !c.p->debug_simt && dx_src != nullptr && gemm_lnbwd_supported(f);
+  const bool fuse_ln = !c.p->debug_simt && dx_src != nullptr && gemm_lnbwd_preferred(f);
   if (fuse_ln) {
     HS_TRY(gemm_tc_lnbwd(f, c.st));
   } else {

@@ -71,7 +71,8 @@ __host__ __device__ inline int packed_col(int which, int h) { return (h / kGate)
 int gemm_tc(const GemmArgs& a, int epi, cudaStream_t stream);
 int gemm_simt(const GemmArgs& a, int epi, float* scratch, cudaStream_t stream);
 int gemm_tc_lnbwd(const GemmArgs& a, cudaStream_t stream);   // kEpiLnBwd
-bool gemm_lnbwd_supported(const GemmArgs& a);   // shapes the fused dgrad + LayerNorm-backward kernel takes (else: two launches)
+bool gemm_lnbwd_supported(const GemmArgs& a);   // shapes the fused dgrad + LayerNorm-backward kernel takes
+bool gemm_lnbwd_preferred(const GemmArgs& a);   // ... and where the engine uses it (else: two launches)
 int wgrad_tc(const WgradArgs& a, cudaStream_t stream);
 int wgrad_tc_group(const WgradArgs* jobs, int njobs, cudaStream_t stream);   // up to 4 independent problems in one launch
 int wgrad_simt(const WgradArgs& a, cudaStream_t stream);

@@ -23,6 +23,8 @@ COMBOS = [
     {"HSIMAE_FUSED_MLP": "0", "HSIMAE_EMBED_MMA": "0"},
     {"HSIMAE_RECOMPUTE_MIN_ROWS": "8192"},
     {"HSIMAE_LNBWD_FUSE": "0"},                                  # dgrad GEMM and LayerNorm backward as two launches
+    {"HSIMAE_LNBWD_MIN_ROWS": "0"},                              # ... and as one kernel at every batch size (default: from two waves of row tiles)
+    {"HSIMAE_LNBWD_MIN_ROWS": "0", "HSIMAE_GEMM_PAIR": "2"},     # ... in its CTA-pair form
     {"HSIMAE_WGRAD_GROUP": "0", "HSIMAE_OVERLAP": "0"},          # ... and both encoder chains on one stream                                 # one weight-gradient launch per problem
 ]
 
