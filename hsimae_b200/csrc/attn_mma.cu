@@ -94,6 +94,14 @@ __device__ __forceinline__ Unit make_unit(const SeqSpec& q, int u) {
   return t;
 }
 
+// Backward works on GROUPS of units that share their key columns: one packed unit, or the ceil(len / 16) row tiles of one
+// (longer) sequence.  dK / dV of a group's keys are accumulated in registers over the group's query units.
+__device__ __forceinline__ int groups_per_head(const SeqSpec& q) {
+  if (q.len <= 8) { const int G = 16 / q.len; return (q.nseq + G - 1) / G; }
+  return q.nseq;
+}
+__device__ __forceinline__ int units_per_group(const SeqSpec& q) { return q.len <= 8 ? 1 : (q.len + 15) / 16; }
+
 __device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_log2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -138,6 +146,51 @@ __device__ __forceinline__ Geo<NT> make_geo(const Unit& t, int lane, int pitch, 
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) { q.c_tok[nt][0] = t.col_token(nt * 8 + 2 * tq); q.c_tok[nt][1] = t.col_token(nt * 8 + 2 * tq + 1); }
   return q;
+}
+
+// Move a Geo to another row tile of the same sequence (same columns): only the row-dependent members change.
+template <int HD, int NT>
+__device__ __forceinline__ void geo_set_rows(Geo<NT>& q, const Unit& t, int lane, int pitch, int pitch_o) {
+  const int mi = lane >> 3, g = lane >> 2, tq = lane & 3;
+  const int a_tok = t.row_token((mi & 1) * 8 + (lane & 7));
+  const int a_co = HD == 8 ? 0 : (mi >> 1) * 8;
+  q.a_off = (uint32_t)(a_tok * pitch + a_co * 2);
+  q.a_off_o = (uint32_t)(a_tok * pitch_o + a_co * 2);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      q.madd[nt][e] = t.pair_valid(g + (e >> 1) * 8, nt * 8 + 2 * tq + (e & 1)) ? 0.f : -INFINITY;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) { q.r_ok[hf] = t.row_valid(g + hf * 8); q.r_tok[hf] = t.row_token(g + hf * 8); }
+}
+
+// token rows of the KEY columns as accumulator rows: key tile kt (16 columns), accumulator rows g, g + 8
+template <int NT>
+struct KeyRows {
+  static constexpr int KT = (NT + 1) / 2;
+  int tok[KT][2]; bool ok[KT][2];
+};
+template <int NT>
+__device__ __forceinline__ KeyRows<NT> make_key_rows(const Unit& t, int lane) {
+  KeyRows<NT> k;
+  const int g = lane >> 2;
+#pragma unroll
+  for (int kt = 0; kt < KeyRows<NT>::KT; ++kt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int c = kt * 16 + hf * 8 + g;
+      k.ok[kt][hf] = c < NT * 8 && t.col_valid(c);
+      k.tok[kt][hf] = t.col_token(c < NT * 8 ? c : 0);
+    }
+  return k;
+}
+
+// transpose of an 8x8 bf16 matrix held as C-fragment pairs (lane: row lane / 4, columns 2 (lane % 4), +1)
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+  uint32_t y;
+  asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
 
 // scores: acc[nt] = rows(A) x cols(B)^T over the head dim.  sA / sB already include the operand's feature column.
@@ -309,14 +362,19 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
 }
 
 // ---------------------------------------------------------------------------
-// backward:  phase 1 (tile rows = queries): dQ;  phase 2 (tile rows = keys): dK, dV
-//   P_ij = exp2(s_ij*c - lse_i),  dS_ij = P_ij (dO_i.V_j - dO_i.O_i) / sqrt(hd)
+// backward, per (group of units sharing their keys, sample, head):
+//   for every 16-row query tile of the group:   P_ij = exp2(s_ij*c - lse_i),  dS_ij = P_ij (dO_i.V_j - dO_i.O_i) / sqrt(hd)
+//     dQ (tile rows) = dS K;   P^T and dS^T come from the SAME accumulator fragments through movmatrix (8x8 transposes),
+//     dK += dS^T Q,  dV += P^T dO  accumulate in registers over the group's query tiles
+//   (the first version recomputed K Q^T, V dO^T and the softmax a second time with keys as tile rows: 6 more MMAs, NT*4 exp2 and
+//    2 NT*4 shared-memory reads of lse / delta per unit and head)
 // ---------------------------------------------------------------------------
 template <int HD, int NT>
 __global__ void __launch_bounds__(kAttnThreads, 3)
 attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_wait();
+  constexpr int KT = (NT + 1) / 2;
   const int D = a.D, K = a.s.K, H = a.heads;
   const int pitch = 3 * D * 2 + 16;
   const int pitch_o = D * 2 + 16;
@@ -326,13 +384,15 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
   float* sdelta = reinterpret_cast<float*>(sdq + (size_t)spc * K * pitch);  // [spc*K][H]
   float* slse = sdelta + (size_t)spc * K * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int tq = lane & 3;
   const float scale = rsqrtf((float)HD);
   const float scale_log2 = scale * 1.4426950408889634f;
-  const int uph = units_per_head(a.s);
+  const int gph = groups_per_head(a.s), upg = units_per_group(a.s);
   const int row_vecs = 3 * D / 8, o_vecs = D / 8;
   const FastDiv fd_row(row_vecs), fd_o(o_vecs), fd_h(H), fd_hg(hgroups);
   Geo<NT> q;
-  int cur_u = -1;
+  KeyRows<NT> kr;
+  int cur_g = -1, cur_i = 0;
 
   for (int n0 = blockIdx.x * spc; n0 < a.N; n0 += gridDim.x * spc) {
     const int ns = (a.N - n0) < spc ? (a.N - n0) : spc;
@@ -373,12 +433,17 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
     }
     __syncthreads();
     const int hpg = H / hgroups;
-    const int total = ns * uph * hgroups;
+    const int total = ns * gph * hgroups;
     const int per_warp = (total + nwarps - 1) / nwarps;
     const int w_end = (warp + 1) * per_warp < total ? (warp + 1) * per_warp : total;
     for (int w = warp * per_warp; w < w_end; ++w) {
-      int wq, hg, u, smp; fd_hg.divmod(w, wq, hg); FastDiv(ns).divmod(wq, u, smp);
-      if (u != cur_u) { q = make_geo<HD, NT>(make_unit(a.s, u), lane, pitch, pitch_o); cur_u = u; }
+      int wq, hg, grp, smp; fd_hg.divmod(w, wq, hg); FastDiv(ns).divmod(wq, grp, smp);
+      if (grp != cur_g) {
+        const Unit t0 = make_unit(a.s, grp * upg);
+        q = make_geo<HD, NT>(t0, lane, pitch, pitch_o);
+        kr = make_key_rows<NT>(t0, lane);
+        cur_g = grp; cur_i = 0;
+      }
       const uint32_t sb = smem_addr(sq + (size_t)smp * K * pitch);
       const uint32_t sdb = smem_addr(sdo + (size_t)smp * K * pitch_o);
       uint8_t* sdq_s = sdq + (size_t)smp * K * pitch;
@@ -386,8 +451,18 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
       const float* ls = slse + (size_t)smp * K * H;
       for (int h = hg * hpg; h < (hg + 1) * hpg; ++h) {
         const uint32_t cq = sb + h * HD * 2, ck = sb + (D + h * HD) * 2, cv = sb + (2 * D + h * HD) * 2, cdo = sdb + h * HD * 2;
-        // ---------------- phase 1: rows = queries
-        {
+        float dk[KT][HD / 8][4], dv[KT][HD / 8][4];
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+          for (int dn = 0; dn < HD / 8; ++dn)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { dk[kt][dn][e] = 0.f; dv[kt][dn][e] = 0.f; }
+        for (int i = 0; i < upg; ++i) {
+          if (i != cur_i) {   // only sequences longer than 16 tokens have more than one row tile
+            geo_set_rows<HD, NT>(q, make_unit(a.s, grp * upg + i), lane, pitch, pitch_o);
+            cur_i = i;
+          }
           float sc[NT][4], dp[NT][4];
           tile_scores<HD, NT>(cq, q.a_off, ck, q.b_off, sc);            // Q K^T
           tile_scores<HD, NT>(cdo, q.a_off_o, cv, q.b_off, dp);         // dO V^T
@@ -400,33 +475,56 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
               const float lse = (e >> 1) ? lse1 : lse0, de = (e >> 1) ? de1 : de0;
               const float p = fast_exp2(fmaf(sc[nt][e], scale_log2, q.madd[nt][e]) - lse);
               sc[nt][e] = p * (dp[nt][e] - de) * scale;     // dS
+              dp[nt][e] = p;                                 // P
             }
           }
-          float dq[HD / 8][4];
-          tile_apply<HD, NT>(sc, ck, q.bc_off, dq);                     // dS K
-          store_tile<HD, NT>(q, dq, 1.f, 1.f, sdq_s, pitch, h * HD, lane);
-        }
-        // ---------------- phase 2: rows = keys, columns = queries
-        {
-          float sc[NT][4], dp[NT][4];
-          tile_scores<HD, NT>(ck, q.a_off, cq, q.b_off, sc);            // K Q^T
-          tile_scores<HD, NT>(cv, q.a_off, cdo, q.b_off_o, dp);         // V dO^T
+          {
+            float dq[HD / 8][4];
+            tile_apply<HD, NT>(sc, ck, q.bc_off, dq);                     // dS K
+            store_tile<HD, NT>(q, dq, 1.f, 1.f, sdq_s, pitch, h * HD, lane);
+          }
+          // dS^T and P^T as A operands: [keys of tile kt] x [the 16 query rows of this tile]
+          uint32_t tS[NT][2], tP[NT][2];
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
+          for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int tc = q.c_tok[nt][e & 1];
-              const float p = fast_exp2(fmaf(sc[nt][e], scale_log2, q.madd[nt][e]) - ls[tc * H + h]);
-              dp[nt][e] = p * (dp[nt][e] - dl[tc * H + h]) * scale;   // dS^T
-              sc[nt][e] = p;                                           // P^T
+            for (int hf = 0; hf < 2; ++hf) {
+              tS[nt][hf] = movm_t(pack_bf16x2(sc[nt][2 * hf], sc[nt][2 * hf + 1]));
+              tP[nt][hf] = movm_t(pack_bf16x2(dp[nt][2 * hf], dp[nt][2 * hf + 1]));
+            }
+#pragma unroll
+          for (int dn = 0; dn < HD / 8; dn += 2) {
+            // B operands (k = the tile's 16 query tokens, n = features): Q and dO rows by transposed ldmatrix
+            uint32_t bq[4], bo[4];
+            ldsm_x4_t(cq + q.a_off + dn * 16, bq[0], bq[1], bq[2], bq[3]);
+            ldsm_x4_t(cdo + q.a_off_o + dn * 16, bo[0], bo[1], bo[2], bo[3]);
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+              const bool two = 2 * kt + 1 < NT;
+              const uint32_t aS[4] = {tS[2 * kt][0], two ? tS[two ? 2 * kt + 1 : 0][0] : 0u, tS[2 * kt][1], two ? tS[two ? 2 * kt + 1 : 0][1] : 0u};
+              const uint32_t aP[4] = {tP[2 * kt][0], two ? tP[two ? 2 * kt + 1 : 0][0] : 0u, tP[2 * kt][1], two ? tP[two ? 2 * kt + 1 : 0][1] : 0u};
+              mma16816(dk[kt][dn], aS, bq[0], bq[1]);                     // dS^T Q
+              mma16816(dv[kt][dn], aP, bo[0], bo[1]);                     // P^T dO
+              if (HD > 8) {
+                mma16816(dk[kt][dn + 1 < HD / 8 ? dn + 1 : dn], aS, bq[2], bq[3]);
+                mma16816(dv[kt][dn + 1 < HD / 8 ? dn + 1 : dn], aP, bo[2], bo[3]);
+              }
             }
           }
-          float dk[HD / 8][4], dv[HD / 8][4];
-          tile_apply<HD, NT>(dp, cq, q.bc_off, dk);                     // dS^T Q
-          tile_apply<HD, NT>(sc, cdo, q.bc_off_o, dv);                  // P^T dO
-          store_tile<HD, NT>(q, dk, 1.f, 1.f, sdq_s, pitch, D + h * HD, lane);
-          store_tile<HD, NT>(q, dv, 1.f, 1.f, sdq_s, pitch, 2 * D + h * HD, lane);
         }
+        // dK, dV of the group's keys: accumulator rows are key columns
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            if (!kr.ok[kt][hf]) continue;
+            uint8_t* row = sdq_s + (size_t)kr.tok[kt][hf] * pitch;
+#pragma unroll
+            for (int dn = 0; dn < HD / 8; ++dn) {
+              *reinterpret_cast<uint32_t*>(row + (D + h * HD + dn * 8 + 2 * tq) * 2) = pack_bf16x2(dk[kt][dn][hf * 2], dk[kt][dn][hf * 2 + 1]);
+              *reinterpret_cast<uint32_t*>(row + (2 * D + h * HD + dn * 8 + 2 * tq) * 2) = pack_bf16x2(dv[kt][dn][hf * 2], dv[kt][dn][hf * 2 + 1]);
+            }
+          }
       }
     }
     __syncthreads();
@@ -442,6 +540,10 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
 int host_units_per_head(const SeqSpec& q) {
   if (q.len <= 8) { const int G = 16 / q.len; return (q.nseq + G - 1) / G; }
   return q.nseq * ((q.len + 15) / 16);
+}
+int host_groups_per_head(const SeqSpec& q) {
+  if (q.len <= 8) { const int G = 16 / q.len; return (q.nseq + G - 1) / G; }
+  return q.nseq;
 }
 int host_col_tiles(const SeqSpec& q) { return q.len <= 8 ? 2 : (q.len + 7) / 8; }
 // smallest divisor of H that gives every warp of the CTA at least two work items
@@ -480,7 +582,7 @@ int bwd_launch_nt(const AttnArgs& a, cudaStream_t stream) {
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
   if (grid > 6 * kNumSMs) grid = 6 * kNumSMs;
-  HS_CHECK_CUDA(launch_pdl(attn_mma_bwd_kernel<HD, NT>, dim3(grid), dim3(kAttnThreads), smem, stream, a, spc, pick_hgroups(a.heads, spc, host_units_per_head(a.s))));
+  HS_CHECK_CUDA(launch_pdl(attn_mma_bwd_kernel<HD, NT>, dim3(grid), dim3(kAttnThreads), smem, stream, a, spc, pick_hgroups(a.heads, spc, host_groups_per_head(a.s))));
   HS_CHECK_LAUNCH("attn_mma_bwd_kernel");
   return kOk;
 }
