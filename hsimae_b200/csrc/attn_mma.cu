@@ -42,6 +42,9 @@ constexpr int kMaxNT = 5;        // key tiles of 8  -> groups of at most 40 toke
 #ifndef HSIMAE_ATTN_FWD_PER_SM
 #define HSIMAE_ATTN_FWD_PER_SM 5
 #endif
+#ifndef HSIMAE_ATTN_BWD_PER_SM
+#define HSIMAE_ATTN_BWD_PER_SM 3
+#endif
 constexpr int kFwdPerSM = HSIMAE_ATTN_FWD_PER_SM;
 constexpr int kAttnThreads = 128;   // small CTAs, several per SM: one CTA's load/store phases overlap the others' math
 
@@ -370,7 +373,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
 //    2 NT*4 shared-memory reads of lse / delta per unit and head)
 // ---------------------------------------------------------------------------
 template <int HD, int NT>
-__global__ void __launch_bounds__(kAttnThreads, 3)
+__global__ void __launch_bounds__(kAttnThreads, HSIMAE_ATTN_BWD_PER_SM)
 attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
   extern __shared__ __align__(16) uint8_t smraw[];
   pdl_wait();
@@ -573,15 +576,15 @@ int fwd_launch_nt(const AttnArgs& a, cudaStream_t stream) {
 template <int HD, int NT>
 int bwd_launch_nt(const AttnArgs& a, cudaStream_t stream) {
   const size_t per_sample = (size_t)a.s.K * (2 * (3 * a.D * 2 + 16) + (a.D * 2 + 16)) + (size_t)a.s.K * a.heads * 8;
-  int spc = (int)((72 * 1024) / per_sample);   // <= 72 KB per CTA: three CTAs per SM
+  int spc = (int)(((216 / HSIMAE_ATTN_BWD_PER_SM) * 1024) / per_sample);   // <= 72 KB per CTA: three CTAs per SM
   if (spc < 1) spc = 1;
-  const int want = ceil_div(a.N, 6 * kNumSMs);
+  const int want = ceil_div(a.N, 2 * HSIMAE_ATTN_BWD_PER_SM * kNumSMs);
   if (spc > want) spc = want < 1 ? 1 : want;
   const size_t smem = per_sample * spc;
   HS_REQUIRE(smem <= 227 * 1024, "attention bwd: %zu bytes of shared memory needed", smem);
   HS_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ceil_div(a.N, spc);
-  if (grid > 6 * kNumSMs) grid = 6 * kNumSMs;
+  if (grid > 2 * HSIMAE_ATTN_BWD_PER_SM * kNumSMs) grid = 2 * HSIMAE_ATTN_BWD_PER_SM * kNumSMs;
   HS_CHECK_CUDA(launch_pdl(attn_mma_bwd_kernel<HD, NT>, dim3(grid), dim3(kAttnThreads), smem, stream, a, spc, pick_hgroups(a.heads, spc, host_groups_per_head(a.s))));
   HS_CHECK_LAUNCH("attn_mma_bwd_kernel");
   return kOk;
