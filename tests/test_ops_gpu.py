@@ -306,7 +306,9 @@ def _attn_ref(qkv, n, D, heads, K, groups):
 @pytest.mark.parametrize("n,D,heads,lt,ll,kind", [
     (37, 256, 16, 3, 6, "spatial"), (37, 256, 16, 3, 6, "spectral"), (37, 256, 16, 3, 6, "full"),
     (20, 256, 16, 2, 9, "spatial"), (20, 256, 16, 2, 9, "spectral"), (300, 64, 8, 4, 9, "full"),
-    (9, 128, 8, 4, 9, "spatial"), (9, 128, 8, 4, 9, "spectral"), (5, 64, 4, 2, 4, "spectral"), (1, 64, 4, 4, 2, "spatial")])
+    (9, 128, 8, 4, 9, "spatial"), (9, 128, 8, 4, 9, "spectral"), (5, 64, 4, 2, 4, "spectral"), (1, 64, 4, 4, 2, "spatial"),
+    # head dimension 32 (two k-steps per score tile), sequences of 18 / 36 / 6 tokens; 3 query tiles with head dimension 16
+    (9, 128, 4, 3, 6, "full"), (7, 256, 8, 4, 9, "full"), (9, 128, 4, 3, 6, "spatial"), (11, 256, 16, 4, 9, "full")])
 def test_attention_fwd_bwd(ops, n, D, heads, lt, ll, kind):
     K = lt * ll
     if kind == "spatial":
