@@ -42,6 +42,14 @@ constexpr int kMaxNT = 5;        // key tiles of 8  -> groups of at most 40 toke
 #ifndef HSIMAE_ATTN_FWD_PER_SM
 #define HSIMAE_ATTN_FWD_PER_SM 5
 #endif
+#ifndef HSIMAE_ATTN_UNROLL_FWD
+#define HSIMAE_ATTN_UNROLL_FWD 1
+#endif
+#ifndef HSIMAE_ATTN_UNROLL_BWD
+#define HSIMAE_ATTN_UNROLL_BWD 1
+#endif
+#define HS_PRAGMA_(x) _Pragma(#x)
+#define HS_UNROLL(n) HS_PRAGMA_(unroll n)
 #ifndef HSIMAE_ATTN_BWD_PER_SM
 #define HSIMAE_ATTN_BWD_PER_SM 3
 #endif
@@ -316,6 +324,7 @@ attn_mma_fwd_kernel(AttnArgs a, int spc, int hgroups) {
       if (u != cur_u) { q = make_geo<HD, NT>(make_unit(a.s, u), lane, pitch, 0); cur_u = u; }
       uint8_t* ssmp = sq + (size_t)smp * K * pitch;
       const uint32_t sb = smem_addr(ssmp);
+HS_UNROLL(HSIMAE_ATTN_UNROLL_FWD)
       for (int h = hg * hpg; h < (hg + 1) * hpg; ++h) {
         float sc[NT][4];
         tile_scores<HD, NT>(sb + h * HD * 2, q.a_off, sb + (D + h * HD) * 2, q.b_off, sc);
@@ -452,6 +461,7 @@ attn_mma_bwd_kernel(AttnArgs a, int spc, int hgroups) {
       uint8_t* sdq_s = sdq + (size_t)smp * K * pitch;
       const float* dl = sdelta + (size_t)smp * K * H;
       const float* ls = slse + (size_t)smp * K * H;
+HS_UNROLL(HSIMAE_ATTN_UNROLL_BWD)
       for (int h = hg * hpg; h < (hg + 1) * hpg; ++h) {
         const uint32_t cq = sb + h * HD * 2, ck = sb + (D + h * HD) * 2, cv = sb + (2 * D + h * HD) * 2, cdo = sdb + h * HD * 2;
         float dk[KT][HD / 8][4], dv[KT][HD / 8][4];

@@ -139,7 +139,8 @@ def test_gemm_resid_layernorm(ops, M, N, K, variant):
             assert torch.allclose(out["stats"][:, 1], (var + 1e-5).rsqrt(), rtol=1e-4)
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 256, 768), (300, 256, 1376), (129, 192, 576), (40000, 256, 768), (77, 160, 64)])
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 768), (300, 256, 1376), (129, 192, 576), (40000, 256, 768), (77, 160, 64),
+                                   (300, 64, 192), (5000, 64, 352), (1000, 32, 64), (1000, 128, 384)])   # decoder-width rows too
 @pytest.mark.parametrize("variant", ["plain", "inplace+scale", "no_dxb"])
 def test_gemm_lnbwd(ops, M, N, K, variant):
     _lnbwd_case(ops, M, N, K, variant)
