@@ -549,9 +549,10 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& p, TmemAcc& acc, Sta
 // output; the tile spans the whole row.  Two passes over the accumulator, sixteen 32-column steps, three fp32 boxes per
 // warp rotating through the copy engine two steps ahead of their use:
 //   pass A (steps 0..7):  box = LayerNorm input x.  xhat = (x - mean) rstd, t = dy gamma; row sums s1 = sum t,
-//                         s2 = sum t xhat; column sums of dy xhat and dy (gradients of gamma / beta) by a butterfly
-//                         exchange across the warp's 32 rows, kept in registers across tiles; (t, xhat) go back into the
-//                         accumulator packed as a bf16 pair (the separate kernel read dy as bf16 too).
+//                         s2 = sum t xhat; column sums of dy xhat and dy (gradients of gamma / beta) over the warp's 32
+//                         rows, transposed through the (now dead) x box and the idle bf16 box (box_colsum), kept in
+//                         registers across tiles; (t, xhat) go back into the accumulator packed as a bf16 pair (the
+//                         separate kernel read dy as bf16 too).
 //   pass B (steps 8..15): box = incoming residual gradient; dx = rstd (t - s1/N - xhat s2/N) + dx_in written in place
 //                         and handed back to TMA as the outgoing residual gradient; bf16(rs dx) -- the next dgrad's
 //                         operand -- through the fourth box, 64 columns per store.
