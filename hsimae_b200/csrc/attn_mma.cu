@@ -71,6 +71,10 @@ struct Unit {
   __device__ __forceinline__ bool row_valid(int r) const {
     return packed ? (r < G * s && seq0 + div_s(r) < nseq) : (pos0 + r < s);
   }
+  // Invalid tile rows are clamped onto the first token of the sequence so that their ldmatrix addresses stay inside the
+  // sample.  In the forward kernel another warp (the unit that owns that token) may be overwriting that token's Q slot with
+  // its O tile at the same time: compute-sanitizer racecheck reports it; the values feed masked scores (madd = -inf) and
+  // rows that are never stored, so either version of the bytes gives the same results.
   __device__ __forceinline__ int row_token(int r) const {   // token row inside the sample (clamped when invalid)
     if (!row_valid(r)) return packed ? seq0 * seq_step : seq0 * seq_step;
     return packed ? (seq0 + div_s(r)) * seq_step + mod_s(r) * tok_step : seq0 * seq_step + (pos0 + r) * tok_step;
