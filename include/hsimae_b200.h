@@ -155,7 +155,8 @@ int hsimae_gemm(const hsimae_gemm_desc* d, void* stream);
  * Models.py:304-305 together with the nn.Linear input gradient that feeds it):
  *   dy = A[M,K] * B[N,K]^T;  dx_out = dx_in + LN_bwd(dy; x, stats = (mean, rstd) per row, gamma);
  *   dxb (optional) = bf16(rowscale * dx_out);  dgamma += sum_rows dy * xhat;  dbeta += sum_rows dy.
- * 128 < N <= 256, N % 32 == 0 (the row has to fit one accumulator tile); dx_in == dx_out is allowed. */
+ * 32 <= N <= 256, N % 32 == 0 (the row has to fit one accumulator tile); dx_in == dx_out is allowed.  The engine uses it from
+ * two waves of 128-row tiles up (HSIMAE_LNBWD_MIN_ROWS), below that the dgrad GEMM and the LayerNorm backward are two launches. */
 typedef struct hsimae_lnbwd_desc {
   int32_t M, N, K;
   const void* A; int32_t lda;
